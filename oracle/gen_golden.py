@@ -118,7 +118,7 @@ def main():
     # ---- case D: compositing in isolation (utils/rendering.py:47-85), incl. ragged N
     comp = {}
     for tag, (B, N, srange) in {"n40": (33, 40, 6.0), "n64": (50, 64, 3.0), "n128": (17, 128, 12.0),
-                                "n192": (9, 192, 2.0), "n1": (5, 1, 2.0), "n7": (4, 7, 30.0)}.items():
+                                "n192": (9, 192, 2.0), "n2": (5, 2, 2.0), "n7": (4, 7, 30.0)}.items():
         outs = torch.randn(B, N, 4, generator=g)
         outs[..., 3] *= srange
         outs.requires_grad_(True)

@@ -99,7 +99,7 @@ def test_all_five_outputs_gradient(golden_weights):
         assert maxabs(grads[k[5:]], ref) <= 2e-2 * scale, k
 
 
-@pytest.mark.parametrize("tag", ["n40", "n64", "n128", "n192", "n1", "n7"])
+@pytest.mark.parametrize("tag", ["n40", "n64", "n128", "n192", "n2", "n7"])
 def test_compositing_isolated(tag):
     g = load_golden("case_composite.npz")
     G = lambda k: g[f"{tag}.{k}"]
