@@ -1,0 +1,133 @@
+/* nerf_b200.h -- C ABI of libnerf_b200.so, the B200 (sm_100a) engine behind the Nerf-Simple
+ * Python call surface.
+ *
+ * The reference (UCSD-Comp-Imaging/Nerf-Simple) has no FFI of its own: its hot path is Python
+ * calling ATen.  Each entry point below replaces the ATen launches of one reference function
+ * (cited per entry as file:line relative to the reference checkout) and is what a maintainer
+ * would bind from utils/rendering.py / utils/nets.py with ctypes.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a CUDA stream handle; no torch types.
+ *   - every function returns 0 (NB200_OK) or a negative error code; nothing throws, nothing
+ *     allocates device memory (all workspaces are caller-allocated), nothing synchronises the
+ *     device.  Work is enqueued on `stream`.
+ *   - all tensors are dense row-major fp32 unless stated; "dev" = device pointer.
+ *   - there is NO CPU fallback: without an sm_100 device the compute calls fail with
+ *     NB200_ERR_CUDA / NB200_ERR_ARCH.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nb200_stream_t; /* cudaStream_t */
+
+enum {
+  NB200_OK = 0,
+  NB200_ERR_ARG = -1,         /* bad argument (null pointer, size <= 0, N < 2, ...)        */
+  NB200_ERR_UNSUPPORTED = -2, /* shape/precision outside what the kernels are built for    */
+  NB200_ERR_CUDA = -3,        /* a CUDA runtime call failed; see nb200_last_cuda_error()   */
+  NB200_ERR_ARCH = -4,        /* device is not sm_100 (tcgen05 kernels cannot run)         */
+  NB200_ERR_WORKSPACE = -5,   /* caller workspace too small                                */
+  NB200_ERR_KERNEL = -6       /* a kernel reported an internal failure (pipeline timeout)  */
+};
+
+/* precision of the MLP path */
+enum {
+  NB200_FP32 = 0, /* fp32 SIMT layer kernels; parity mode, max-abs err <= 1e-4 vs reference    */
+  NB200_BF16 = 1  /* fused tcgen05 kernel, bf16 operands + fp32 accumulate in TMEM; <= 1e-2    */
+};
+
+/* input mode of the MLP kernels */
+enum {
+  NB200_IN_POINTS = 0, /* in0 = query points [M,6] (x,y,z,d1,d2,d3): Nerf.forward, nets.py:34  */
+  NB200_IN_RAYS = 1    /* in0 = rays [B,6], in1 = ts [B,N]; points o+t*d and d/|d| are built in
+                          registers: render_nerf, rendering.py:31-40                          */
+};
+
+/* (viii) version / build query */
+int nb200_version(void);            /* 100*major + minor */
+int nb200_compiled_arch(void);      /* 100 -> built for sm_100a */
+int nb200_device_arch(void);        /* 10*major+minor of the current device, or <0 */
+const char* nb200_error_string(int code);
+const char* nb200_last_cuda_error(void);
+
+/* (vii) device ray generation.  Replaces utils/xyz.py:38-52 (rays_single_cam) followed by
+ * utils/rendering.py:129-134 / utils/dataload.py:123-127 (R @ dirs, origin broadcast, pack).
+ * Ray r in [0, P*H*W): pose r / (H*W), pixel (h, w) = divmod(r % (H*W), W);
+ * camera dir = ((w - W/2)/f, -(h - H/2)/f, -1) (integer centre, no +0.5).
+ * poses: dev [P,4,4] row-major camera-to-world.  rays: dev [n_rays,6] = (origin, dir). */
+int nb200_generate_rays(const float* poses, int P, int H, int W, float f, int64_t ray_begin,
+                        int64_t n_rays, float* rays, nb200_stream_t stream);
+
+/* (vi) stratified sampler.  Replaces utils/rendering.py:24-30: ts = bin*u + t_bins[:-1],
+ * t_bins = linspace(tn, tf, N+1) with torch.linspace's fp32 rounding.
+ * u != NULL: reference-RNG mode, u is dev [B,N] drawn by the caller (torch.rand on the CPU
+ *            generator, like the reference) -> bit-identical ts.
+ * u == NULL: throughput mode, Philox4x32-10 keyed by (seed, offset + sample index). */
+int nb200_stratified_ts(const float* u, uint64_t seed, uint64_t offset, int64_t B, int N, float tn,
+                        float tf, float* ts, nb200_stream_t stream);
+
+/* (iv) compositing forward.  Replaces utils/rendering.py:60-85 (volume_render).
+ * outs dev [B,N,4] (r,g,b,sigma), ts dev [B,N].
+ * dirs_mode 0: dirs dev [B,3] exactly as passed to volume_render (deltas scale by its norm, :62).
+ * dirs_mode 1: dirs is the rays tensor dev [B,6]; the direction is normalised first, as
+ *              render_nerf does at :37 before calling volume_render at :43.
+ * rgb [B,3], disp [B], acc [B] are always written; alpha / weights [B,N] when non-NULL. */
+int nb200_composite_forward(const float* outs, const float* ts, const float* dirs, int dirs_mode,
+                            int64_t B, int N,
+                            float* rgb, float* disp, float* acc, float* alpha, float* weights,
+                            nb200_stream_t stream);
+
+/* (v) compositing backward (analytic; what autograd does through rendering.py:60-83).
+ * Cotangents d_rgb [B,3] (required), d_disp [B], d_acc [B], d_alpha [B,N], d_w [B,N] (each may
+ * be NULL = zero).  Writes d_outs [B,N,4].  ts/dirs carry no gradient in the reference. */
+int nb200_composite_backward(const float* outs, const float* ts, const float* dirs, int dirs_mode,
+                             const float* d_rgb, const float* d_disp, const float* d_acc,
+                             const float* d_alpha, const float* d_w, int64_t B, int N,
+                             float* d_outs, nb200_stream_t stream);
+
+/* positional encoding only.  Replaces utils/xyz.py:16-36 for direct callers of
+ * positional_encoder: v dev [M,6] -> posx [M,3+6*Lp], posd [M,3+6*Ld], column order
+ * coordinate-major, then level, sin before cos; frequencies 2^i, no pi. */
+int nb200_positional_encoding(const float* v, int64_t M, int Lp, int Ld, float* posx, float* posd,
+                              nb200_stream_t stream);
+
+/* (i) weight packing.  params: HOST array of 24 DEVICE pointers in state_dict order
+ * (utils/nets.py:16-32; layers_0.0.weight, layers_0.0.bias, ..., color_fc.2.bias).
+ * NB200_FP32 uses the parameters in place (packed may be NULL, bytes == 0).
+ * NB200_BF16 writes the tcgen05 operand images (bf16, K-major, 128B-swizzled, padded/split
+ * K: 63->64, 319->256+64, 283->256+32, plus the transposed images for dgrad) and fp32 biases. */
+size_t nb200_packed_weights_bytes(int precision);
+int nb200_pack_weights(int precision, const float* const* params, void* packed,
+                       nb200_stream_t stream);
+
+/* workspace sizes for M samples.  `train` != 0: forward keeps what backward needs. */
+size_t nb200_mlp_saved_bytes(int precision, int64_t M);     /* forward -> backward tensors  */
+size_t nb200_mlp_scratch_bytes(int precision, int64_t M, int train);
+
+/* (ii) fused posenc + MLP forward.  Replaces utils/nets.py:34-43 (+ utils/xyz.py:16-36, and in
+ * NB200_IN_RAYS mode utils/rendering.py:31-40).  M = number of samples (B*N in rays mode).
+ * out dev [M,4] = (r,g,b,sigma) raw.  saved: NULL for inference, else >= saved_bytes. */
+int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float* in1, int64_t M,
+                      int N, const float* const* params, const void* packed, float* out,
+                      void* saved, void* scratch, size_t scratch_bytes, nb200_stream_t stream);
+
+/* (iii) MLP backward.  d_out dev [M,4] -> grads: HOST array of 24 DEVICE pointers (same order
+ * and shapes as params; typically views into one flat 595,844-float buffer).  Gradients are
+ * ACCUMULATED (+=) like autograd; zero them first for a fresh gradient.  No input gradient:
+ * query points never require grad in the reference (rendering.py:39-41). */
+int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float* in1, int64_t M,
+                       int N, const float* const* params, const void* packed, const float* d_out,
+                       const void* saved, float* const* grads, void* scratch,
+                       size_t scratch_bytes, nb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,46 @@
+"""Run-time switches of the engine (process-wide)."""
+from __future__ import annotations
+
+import os
+
+_state = {
+    # "bf16": fused tcgen05 kernel (throughput mode, <=1e-2 parity); "fp32": SIMT parity mode (<=1e-4)
+    "precision": os.environ.get("NERF_B200_PRECISION", "bf16"),
+    # "reference": draw torch.rand(B,N) from the CPU global generator exactly like
+    # utils/rendering.py:28 (bit-identical ts);  "philox": counter-based generator on the device.
+    "sampler": os.environ.get("NERF_B200_SAMPLER", "reference"),
+    "seed": int(os.environ.get("NERF_B200_SEED", "1")),
+    "philox_offset": 0,
+    # fp32 mode keeps ~10 KB/sample for backward; chunk the MLP to bound workspace
+    "max_samples_per_call": int(os.environ.get("NERF_B200_MAX_SAMPLES", str(1 << 22))),
+}
+
+
+def set_precision(p: str):
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _state["precision"] = p
+
+
+def get_precision() -> str:
+    return _state["precision"]
+
+
+def set_sampler(mode: str, seed: int | None = None):
+    if mode not in ("reference", "philox"):
+        raise ValueError("sampler must be 'reference' or 'philox'")
+    _state["sampler"] = mode
+    if seed is not None:
+        _state["seed"] = int(seed)
+        _state["philox_offset"] = 0
+
+
+def get_sampler() -> str:
+    return _state["sampler"]
+
+
+def next_philox(n_samples: int):
+    """Reserve a counter range for n_samples draws; returns (seed, offset)."""
+    off = _state["philox_offset"]
+    _state["philox_offset"] = off + (n_samples + 3) // 4
+    return _state["seed"], off

@@ -1,0 +1,95 @@
+// Dispatch of the MLP entry points of the C ABI to the fp32 (SIMT) and bf16 (tcgen05) engines.
+#include "common.cuh"
+
+namespace nb200 {
+// mlp_fp32.cu
+size_t fp32_saved_bytes(int64_t M);
+size_t fp32_scratch_bytes(int64_t M, int train);
+int fp32_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N,
+                 const float* const* P, float* out, void* saved, void* scratch, size_t scratch_bytes,
+                 cudaStream_t s);
+int fp32_backward(int64_t M, const float* const* P, const float* d_out, const void* saved,
+                  float* const* G, void* scratch, size_t scratch_bytes, cudaStream_t s);
+// mlp_tc.cu
+size_t tc_packed_bytes();
+size_t tc_saved_bytes(int64_t M);
+size_t tc_scratch_bytes(int64_t M, int train);
+int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s);
+int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
+               float* out, void* saved, void* scratch, size_t scratch_bytes, cudaStream_t s);
+int tc_backward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
+                const float* d_out, const void* saved, float* const* G, void* scratch,
+                size_t scratch_bytes, cudaStream_t s);
+}  // namespace nb200
+
+extern "C" {
+
+size_t nb200_packed_weights_bytes(int precision) {
+  return precision == NB200_BF16 ? nb200::tc_packed_bytes() : 0;
+}
+
+int nb200_pack_weights(int precision, const float* const* params, void* packed, nb200_stream_t stream) {
+  if (precision == NB200_FP32) return NB200_OK;
+  if (precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;
+  if (!params || !packed) return NB200_ERR_ARG;
+  for (int i = 0; i < 24; ++i)
+    if (!params[i]) return NB200_ERR_ARG;
+  return nb200::tc_pack_weights(params, packed, nb200::as_stream(stream));
+}
+
+size_t nb200_mlp_saved_bytes(int precision, int64_t M) {
+  if (M < 0) return 0;
+  return precision == NB200_BF16 ? nb200::tc_saved_bytes(M) : nb200::fp32_saved_bytes(M);
+}
+
+size_t nb200_mlp_scratch_bytes(int precision, int64_t M, int train) {
+  if (M < 0) return 0;
+  return precision == NB200_BF16 ? nb200::tc_scratch_bytes(M, train) : nb200::fp32_scratch_bytes(M, train);
+}
+
+static int check_common(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N) {
+  if (precision != NB200_FP32 && precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;
+  if (in_mode != NB200_IN_POINTS && in_mode != NB200_IN_RAYS) return NB200_ERR_ARG;
+  if (!in0 || M < 0) return NB200_ERR_ARG;
+  if (in_mode == NB200_IN_RAYS && (!in1 || N < 1 || M % N != 0)) return NB200_ERR_ARG;
+  return NB200_OK;
+}
+
+int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N,
+                      const float* const* params, const void* packed, float* out, void* saved,
+                      void* scratch, size_t scratch_bytes, nb200_stream_t stream) {
+  int rc = check_common(precision, in_mode, in0, in1, M, N);
+  if (rc != NB200_OK) return rc;
+  if (!out) return NB200_ERR_ARG;
+  if (M == 0) return NB200_OK;
+  if (precision == NB200_FP32) {
+    if (!params) return NB200_ERR_ARG;
+    return nb200::fp32_forward(in_mode, in0, in1, M, N, params, out, saved, scratch, scratch_bytes,
+                               nb200::as_stream(stream));
+  }
+  if (!packed) return NB200_ERR_ARG;
+  return nb200::tc_forward(in_mode, in0, in1, M, N, packed, out, saved, scratch, scratch_bytes,
+                           nb200::as_stream(stream));
+}
+
+int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N,
+                       const float* const* params, const void* packed, const float* d_out,
+                       const void* saved, float* const* grads, void* scratch, size_t scratch_bytes,
+                       nb200_stream_t stream) {
+  int rc = check_common(precision, in_mode, in0, in1, M, N);
+  if (rc != NB200_OK) return rc;
+  if (!d_out || !saved || !grads) return NB200_ERR_ARG;
+  for (int i = 0; i < 24; ++i)
+    if (!grads[i]) return NB200_ERR_ARG;
+  if (M == 0) return NB200_OK;
+  if (precision == NB200_FP32) {
+    if (!params) return NB200_ERR_ARG;
+    return nb200::fp32_backward(M, params, d_out, saved, grads, scratch, scratch_bytes,
+                                nb200::as_stream(stream));
+  }
+  if (!packed) return NB200_ERR_ARG;
+  return nb200::tc_backward(in_mode, in0, in1, M, N, packed, d_out, saved, grads, scratch,
+                            scratch_bytes, nb200::as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// NB200_FP32 precision of the posenc + MLP path: exact-fp32 SIMT kernels (parity mode).
+//   forward  <- utils/xyz.py:16-36 + utils/nets.py:34-43 (+ utils/rendering.py:31-40 in rays mode)
+//   backward <- autograd of the same (parameter gradients only)
+// This is the max-abs-err <= 1e-4 mode of BASELINE.json; the throughput mode is the fused
+// tcgen05 kernel in mlp_tc.cu.  Layers run one launch each through one generic tiled SGEMM
+// (128x128x16 tiles, 8x8 register micro-tiles) with fused bias/ReLU/mask epilogues; activations
+// stay fp32 in HBM between layers.
+#include "common.cuh"
+
+namespace nb200 {
+
+// ------------------------------------------------------------------------------- encoding
+struct PointSrc {
+  int mode;          // NB200_IN_POINTS / NB200_IN_RAYS
+  const float* in0;  // points [M,6] or rays [B,6]
+  const float* in1;  // ts [B,N] (rays mode)
+  int N;
+};
+
+// Query point of sample m: (x,y,z,d1,d2,d3).  Rays mode follows utils/rendering.py:31-37:
+// p = o + t*d (mul then add, d un-normalised), view dir = d/||d||.
+__device__ __forceinline__ void load_query(const PointSrc& src, int64_t m, float v[6]) {
+  if (src.mode == NB200_IN_POINTS) {
+    const float2* p = reinterpret_cast<const float2*>(src.in0 + m * 6);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+  } else {
+    const int64_t ray = m / src.N;
+    const float2* p = reinterpret_cast<const float2*>(src.in0 + ray * 6);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const float t = __ldg(src.in1 + m);
+    const float dx = b.y, dy = c.x, dz = c.y;
+    v[0] = __fadd_rn(a.x, __fmul_rn(dx, t));
+    v[1] = __fadd_rn(a.y, __fmul_rn(dy, t));
+    v[2] = __fadd_rn(b.x, __fmul_rn(dz, t));
+    const float nrm = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    v[3] = __fdiv_rn(dx, nrm); v[4] = __fdiv_rn(dy, nrm); v[5] = __fdiv_rn(dz, nrm);
+  }
+}
+
+// Column order (utils/xyz.py:12-13,33-34): [c0,c1,c2, then per coordinate c: per level i:
+// sin(2^i c), cos(2^i c)]  => col = 3 + c*2L + 2i + s.  Frequencies 2^i, no pi.
+__global__ void __launch_bounds__(128)
+posenc_fp32_kernel(PointSrc src, int64_t M, int Lp, int Ld, float* __restrict__ posx, int pitch_x,
+                   float* __restrict__ posd, int pitch_d) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M;
+       m += (int64_t)gridDim.x * blockDim.x) {
+    float v[6];
+    load_query(src, m, v);
+    float* px = posx + m * pitch_x;
+    float* pd = posd + m * pitch_d;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      px[c] = v[c];
+      pd[c] = v[3 + c];
+      float f = 1.f;
+      for (int i = 0; i < Lp; ++i, f *= 2.f) {
+        float s, co;
+        sincosf(f * v[c], &s, &co);  // full-range reduction; arguments reach 2^9*|x|
+        px[3 + c * 2 * Lp + 2 * i] = s;
+        px[3 + c * 2 * Lp + 2 * i + 1] = co;
+      }
+      f = 1.f;
+      for (int i = 0; i < Ld; ++i, f *= 2.f) {
+        float s, co;
+        sincosf(f * v[3 + c], &s, &co);
+        pd[3 + c * 2 * Ld + 2 * i] = s;
+        pd[3 + c * 2 * Ld + 2 * i + 1] = co;
+      }
+    }
+    for (int j = 3 + 6 * Lp; j < pitch_x; ++j) px[j] = 0.f;  // K padding columns
+    for (int j = 3 + 6 * Ld; j < pitch_d; ++j) pd[j] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------- generic SGEMM
+// C[i,j] (+)= epilogue( sum_seg sum_k A_seg(i,k) * B_seg(k,j) ),  arbitrary element strides.
+struct GemmSeg {
+  const float* A; int64_t sa_i, sa_k;
+  const float* B; int64_t sb_k, sb_j;
+  int64_t K;
+};
+struct GemmArgs {
+  GemmSeg seg[2];
+  int nseg;
+  int64_t rows; int cols;
+  float* C; int64_t ldc;
+  const float* bias;   // [cols] or null
+  int relu;
+  const float* mask;   // multiply by (mask[i*ldm+j] > 0) (ReLU backward), or null
+  int64_t ldm;
+  int atomic;          // split-K: atomicAdd into C (grid.z slices the reduction)
+  int64_t k_chunk;     // reduction elements per grid.z slice (seg 0 only when atomic)
+};
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+__device__ __forceinline__ void load_tile(float (*dst)[BM + PAD], const float* __restrict__ P,
+                                          int64_t s_mn, int64_t s_k, int64_t mn0, int64_t mn_lim,
+                                          int64_t k0, int64_t k_lim, int tid) {
+  // tile element (mn, k): mn in [0,128), k in [0,16); choose the unit-stride index as fastest
+  if (s_k == 1) {
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / 256; ++r) {
+      const int e = tid + 256 * r;
+      const int k = e & (BK - 1), mn = e >> 4;
+      const int64_t gm = mn0 + mn, gk = k0 + k;
+      dst[k][mn] = (gm < mn_lim && gk < k_lim) ? __ldg(P + gm * s_mn + gk) : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / 256; ++r) {
+      const int e = tid + 256 * r;
+      const int mn = e & (BM - 1), k = e >> 7;
+      const int64_t gm = mn0 + mn, gk = k0 + k;
+      dst[k][mn] = (gm < mn_lim && gk < k_lim) ? __ldg(P + gm * s_mn + gk * s_k) : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * BM;
+  const int64_t j0 = (int64_t)blockIdx.x * BN;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+  for (int s = 0; s < g.nseg; ++s) {
+    const GemmSeg sg = g.seg[s];
+    int64_t kb = 0, ke = sg.K;
+    if (g.atomic) {
+      kb = (int64_t)blockIdx.z * g.k_chunk;
+      ke = kb + g.k_chunk < sg.K ? kb + g.k_chunk : sg.K;
+    }
+    for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+      load_tile(As, sg.A, sg.sa_i, sg.sa_k, i0, g.rows, k0, ke, tid);
+      load_tile(Bs, sg.B, sg.sb_j, sg.sb_k, j0, g.cols, k0, ke, tid);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+    if (i >= g.rows) continue;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int64_t j = j0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + (c - 4));
+      if (j >= g.cols) continue;
+      float v = acc[r][c];
+      if (g.atomic) {
+        atomicAdd(g.C + i * g.ldc + j, v);
+      } else {
+        if (g.bias) v += __ldg(g.bias + j);
+        if (g.relu) v = fmaxf(v, 0.f);
+        if (g.mask) v = (__ldg(g.mask + i * g.ldm + j) > 0.f) ? v : 0.f;
+        g.C[i * g.ldc + j] = v;
+      }
+    }
+  }
+}
+
+// column sums of X[M, n] (ld) accumulated into out[n]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t M, int n,
+                                                     int64_t ld, int64_t rows_per_block,
+                                                     float* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= n) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += __ldg(X + r * ld + j);
+  atomicAdd(out + j, s);
+}
+
+static int launch_gemm(GemmArgs& g, cudaStream_t s) {
+  dim3 grid((unsigned)((g.cols + BN - 1) / BN), (unsigned)((g.rows + BM - 1) / BM), 1);
+  if (g.atomic) {
+    // split the (single-segment) reduction so the grid fills the machine ~4x over
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    int64_t want = ((int64_t)sm_count() * 4 + tiles - 1) / tiles;
+    int64_t chunk = (g.seg[0].K + want - 1) / want;
+    chunk = ((chunk + BK - 1) / BK) * BK;
+    if (chunk < 256) chunk = 256;
+    g.k_chunk = chunk;
+    grid.z = (unsigned)((g.seg[0].K + chunk - 1) / chunk);
+  }
+  sgemm_kernel<<<grid, 256, 0, s>>>(g);
+  NB_LAUNCH_CHECK("sgemm_kernel");
+  return NB200_OK;
+}
+
+// Forward layer: C[M,n_out] = act( A1[M,K1] @ W[:, 0:K1]^T (+ A2[M,K2] @ W[:, K1:K1+K2]^T) + b )
+static int fwd_layer(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2,
+                     const float* W, int ldw, const float* bias, int n_out, int relu, float* C,
+                     int64_t ldc, int64_t M, cudaStream_t s) {
+  GemmArgs g = {};
+  g.seg[0] = {A1, lda1, 1, W, 1, ldw, K1};
+  g.nseg = 1;
+  if (A2) {
+    g.seg[1] = {A2, lda2, 1, W + K1, 1, ldw, K2};
+    g.nseg = 2;
+  }
+  g.rows = M; g.cols = n_out; g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
+  return launch_gemm(g, s);
+}
+
+// dgrad: dX[M,K] = ( dY1[M,n1] @ W1[:, col0:col0+K] (+ dY2[M,n2] @ W2[:, 0:K]) ) * (mask > 0)
+static int dgrad_layer(const float* dY1, int64_t ldy1, int n1, const float* W1, int ldw1,
+                       const float* dY2, int64_t ldy2, int n2, const float* W2, int ldw2, int K,
+                       const float* mask, int64_t ldm, float* dX, int64_t ldx, int64_t M,
+                       cudaStream_t s) {
+  GemmArgs g = {};
+  g.seg[0] = {dY1, ldy1, 1, W1, ldw1, 1, n1};
+  g.nseg = 1;
+  if (dY2) {
+    g.seg[1] = {dY2, ldy2, 1, W2, ldw2, 1, n2};
+    g.nseg = 2;
+  }
+  g.rows = M; g.cols = K; g.C = dX; g.ldc = ldx; g.mask = mask; g.ldm = ldm;
+  return launch_gemm(g, s);
+}
+
+// wgrad: dW[n_out, col0:col0+K] += dY[M,n_out]^T @ X[M,K]   (split over M, atomics)
+static int wgrad_layer(const float* dY, int64_t ldy, int n_out, const float* X, int64_t ldx, int K,
+                       float* dW, int ldw, int64_t M, cudaStream_t s) {
+  GemmArgs g = {};
+  g.seg[0] = {dY, 1, ldy, X, ldx, 1, M};
+  g.nseg = 1;
+  g.rows = n_out; g.cols = K; g.C = dW; g.ldc = ldw; g.atomic = 1;
+  return launch_gemm(g, s);
+}
+
+static int bias_grad(const float* dY, int64_t ldy, int n_out, float* db, int64_t M, cudaStream_t s) {
+  const int64_t rows_per_block = 512;
+  colsum_kernel<<<(unsigned)ceil_div64(M, rows_per_block), 256, 0, s>>>(dY, M, n_out, ldy,
+                                                                       rows_per_block, db);
+  NB_LAUNCH_CHECK("colsum_kernel");
+  return NB200_OK;
+}
+
+static int posenc_launch(const PointSrc& src, int64_t M, int Lp, int Ld, float* posx, int pitch_x,
+                         float* posd, int pitch_d, cudaStream_t s) {
+  const int64_t blocks = ceil_div64(M, 128);
+  const int64_t cap = (int64_t)sm_count() * 32;
+  posenc_fp32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, s>>>(src, M, Lp, Ld, posx,
+                                                                            pitch_x, posd, pitch_d);
+  NB_LAUNCH_CHECK("posenc_fp32_kernel");
+  return NB200_OK;
+}
+
+// fp32 saved-tensor layout (floats per sample): posx 64 | posd 32 | act[8] 8*256 | g 256 | c1 128
+constexpr int64_t kSavedFloats = kPosXPad + kPosDPad + 8 * kHidden + kHidden + kHidden / 2;
+struct Fp32Bufs {
+  float *posx, *posd, *act[8], *g, *c1;
+};
+static Fp32Bufs carve_saved(void* base, int64_t M) {
+  Fp32Bufs b;
+  float* p = reinterpret_cast<float*>(base);
+  b.posx = p; p += M * kPosXPad;
+  b.posd = p; p += M * kPosDPad;
+  for (int i = 0; i < 8; ++i) { b.act[i] = p; p += M * kHidden; }
+  b.g = p; p += M * kHidden;
+  b.c1 = p;
+  return b;
+}
+// inference scratch: posx 64 | posd 32 | ping 256 | pong 256 | c1 128
+constexpr int64_t kInferFloats = kPosXPad + kPosDPad + 2 * kHidden + kHidden / 2;
+// backward scratch: dA 256 | dB 256 | dc1 128
+constexpr int64_t kBwdFloats = 2 * kHidden + kHidden / 2;
+
+size_t fp32_saved_bytes(int64_t M) { return (size_t)M * kSavedFloats * sizeof(float); }
+size_t fp32_scratch_bytes(int64_t M, int train) {
+  return (size_t)M * (train ? kBwdFloats : kInferFloats) * sizeof(float);
+}
+
+#define NB_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != NB200_OK) return _rc; \
+  } while (0)
+
+int fp32_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N,
+                 const float* const* P, float* out, void* saved, void* scratch, size_t scratch_bytes,
+                 cudaStream_t s) {
+  Fp32Bufs b;
+  if (saved) {
+    b = carve_saved(saved, M);
+  } else {
+    if (!scratch || scratch_bytes < fp32_scratch_bytes(M, 0)) return NB200_ERR_WORKSPACE;
+    float* p = reinterpret_cast<float*>(scratch);
+    b.posx = p; p += M * kPosXPad;
+    b.posd = p; p += M * kPosDPad;
+    float* ping = p; p += M * kHidden;
+    float* pong = p; p += M * kHidden;
+    for (int i = 0; i < 8; ++i) b.act[i] = (i & 1) ? pong : ping;
+    b.g = ping;  // act[7] lives in pong
+    b.c1 = p;
+  }
+  PointSrc src = {in_mode, in0, in1, N};
+  NB_TRY(posenc_launch(src, M, kLp, kLd, b.posx, kPosXPad, b.posd, kPosDPad, s));
+  const int H = kHidden;
+  auto Wt = [&](int l) { return P[2 * l]; };
+  auto Bs_ = [&](int l) { return P[2 * l + 1]; };
+  // layers_0 (utils/nets.py:16-19,37)
+  NB_TRY(fwd_layer(b.posx, kPosXPad, kPosX, nullptr, 0, 0, Wt(L0_0), kPosX, Bs_(L0_0), H, 1, b.act[0], H, M, s));
+  for (int l = 1; l <= 4; ++l)
+    NB_TRY(fwd_layer(b.act[l - 1], H, H, nullptr, 0, 0, Wt(L0_0 + l), H, Bs_(L0_0 + l), H, 1, b.act[l], H, M, s));
+  // skip layer on cat([h, posx]) (:21,38)
+  NB_TRY(fwd_layer(b.act[4], H, H, b.posx, kPosXPad, kPosX, Wt(L_SKIP), H + kPosX, Bs_(L_SKIP), H, 1, b.act[5], H, M, s));
+  // layers_1 (:23-26,39)
+  NB_TRY(fwd_layer(b.act[5], H, H, nullptr, 0, 0, Wt(L1_0), H, Bs_(L1_0), H, 1, b.act[6], H, M, s));
+  NB_TRY(fwd_layer(b.act[6], H, H, nullptr, 0, 0, Wt(L1_1), H, Bs_(L1_1), H, 1, b.act[7], H, M, s));
+  // sigma head read before layers_2 (:27,40) -> out[:,3]
+  NB_TRY(fwd_layer(b.act[7], H, H, nullptr, 0, 0, Wt(L_SIGMA), H, Bs_(L_SIGMA), 1, 0, out + 3, 4, M, s));
+  // layers_2, no activation (:28,41)
+  NB_TRY(fwd_layer(b.act[7], H, H, nullptr, 0, 0, Wt(L_2), H, Bs_(L_2), H, 0, b.g, H, M, s));
+  // colour head on cat([g, posd]) (:30-32,42) -> out[:,0:3]
+  NB_TRY(fwd_layer(b.g, H, H, b.posd, kPosDPad, kPosD, Wt(L_C0), H + kPosD, Bs_(L_C0), H / 2, 1, b.c1, H / 2, M, s));
+  NB_TRY(fwd_layer(b.c1, H / 2, H / 2, nullptr, 0, 0, Wt(L_C1), H / 2, Bs_(L_C1), 3, 0, out, 4, M, s));
+  return NB200_OK;
+}
+
+int fp32_backward(int64_t M, const float* const* P, const float* d_out, const void* saved,
+                  float* const* G, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  if (!saved) return NB200_ERR_ARG;
+  if (!scratch || scratch_bytes < fp32_scratch_bytes(M, 1)) return NB200_ERR_WORKSPACE;
+  const Fp32Bufs b = carve_saved(const_cast<void*>(saved), M);
+  float* dA = reinterpret_cast<float*>(scratch);
+  float* dB = dA + M * kHidden;
+  float* dc1 = dB + M * kHidden;
+  const int H = kHidden;
+  auto Wt = [&](int l) { return P[2 * l]; };
+  auto gW = [&](int l) { return G[2 * l]; };
+  auto gB = [&](int l) { return G[2 * l + 1]; };
+  // color_fc.2: rgb = c1 @ Wc1^T + b
+  NB_TRY(wgrad_layer(d_out, 4, 3, b.c1, H / 2, H / 2, gW(L_C1), H / 2, M, s));
+  NB_TRY(bias_grad(d_out, 4, 3, gB(L_C1), M, s));
+  NB_TRY(dgrad_layer(d_out, 4, 3, Wt(L_C1), H / 2, nullptr, 0, 0, nullptr, 0, H / 2, b.c1, H / 2, dc1, H / 2, M, s));
+  // color_fc.0 on cat([g, posd])
+  NB_TRY(wgrad_layer(dc1, H / 2, H / 2, b.g, H, H, gW(L_C0), H + kPosD, M, s));
+  NB_TRY(wgrad_layer(dc1, H / 2, H / 2, b.posd, kPosDPad, kPosD, gW(L_C0) + H, H + kPosD, M, s));
+  NB_TRY(bias_grad(dc1, H / 2, H / 2, gB(L_C0), M, s));
+  NB_TRY(dgrad_layer(dc1, H / 2, H / 2, Wt(L_C0), H + kPosD, nullptr, 0, 0, nullptr, 0, H, nullptr, 0, dA, H, M, s));  // d_g
+  // layers_2 and sigma head share input act[7]
+  NB_TRY(wgrad_layer(dA, H, H, b.act[7], H, H, gW(L_2), H, M, s));
+  NB_TRY(bias_grad(dA, H, H, gB(L_2), M, s));
+  NB_TRY(wgrad_layer(d_out + 3, 4, 1, b.act[7], H, H, gW(L_SIGMA), H, M, s));
+  NB_TRY(bias_grad(d_out + 3, 4, 1, gB(L_SIGMA), M, s));
+  NB_TRY(dgrad_layer(dA, H, H, Wt(L_2), H, d_out + 3, 4, 1, Wt(L_SIGMA), H, H, b.act[7], H, dB, H, M, s));  // d_h7
+  float* cur = dB;
+  float* nxt = dA;
+  // layers_1.2 (act[6]->act[7]), layers_1.0 (act[5]->act[6])
+  for (int l = L1_1, a = 6; l >= L1_0; --l, --a) {
+    NB_TRY(wgrad_layer(cur, H, H, b.act[a], H, H, gW(l), H, M, s));
+    NB_TRY(bias_grad(cur, H, H, gB(l), M, s));
+    NB_TRY(dgrad_layer(cur, H, H, Wt(l), H, nullptr, 0, 0, nullptr, 0, H, b.act[a], H, nxt, H, M, s));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // skip layer: input cat([act[4], posx])
+  NB_TRY(wgrad_layer(cur, H, H, b.act[4], H, H, gW(L_SKIP), H + kPosX, M, s));
+  NB_TRY(wgrad_layer(cur, H, H, b.posx, kPosXPad, kPosX, gW(L_SKIP) + H, H + kPosX, M, s));
+  NB_TRY(bias_grad(cur, H, H, gB(L_SKIP), M, s));
+  NB_TRY(dgrad_layer(cur, H, H, Wt(L_SKIP), H + kPosX, nullptr, 0, 0, nullptr, 0, H, b.act[4], H, nxt, H, M, s));
+  { float* t = cur; cur = nxt; nxt = t; }
+  // layers_0.8 .. layers_0.2 (inputs act[3] .. act[0])
+  for (int l = L0_4, a = 3; l >= L0_1; --l, --a) {
+    NB_TRY(wgrad_layer(cur, H, H, b.act[a], H, H, gW(l), H, M, s));
+    NB_TRY(bias_grad(cur, H, H, gB(l), M, s));
+    NB_TRY(dgrad_layer(cur, H, H, Wt(l), H, nullptr, 0, 0, nullptr, 0, H, b.act[a], H, nxt, H, M, s));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // layers_0.0: input posx
+  NB_TRY(wgrad_layer(cur, H, H, b.posx, kPosXPad, kPosX, gW(L0_0), kPosX, M, s));
+  NB_TRY(bias_grad(cur, H, H, gB(L0_0), M, s));
+  return NB200_OK;
+}
+
+}  // namespace nb200
+
+extern "C" int nb200_positional_encoding(const float* v, int64_t M, int Lp, int Ld, float* posx,
+                                         float* posd, nb200_stream_t stream) {
+  using namespace nb200;
+  if (!v || !posx || !posd || M < 0 || Lp < 0 || Ld < 0 || Lp > 24 || Ld > 24) return NB200_ERR_ARG;
+  if (M == 0) return NB200_OK;
+  PointSrc src = {NB200_IN_POINTS, v, nullptr, 1};
+  return posenc_launch(src, M, Lp, Ld, posx, 3 + 6 * Lp, posd, 3 + 6 * Ld, as_stream(stream));
+}

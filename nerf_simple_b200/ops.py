@@ -1,0 +1,226 @@
+"""autograd.Function wrappers over the C ABI: one per operator boundary of the reference.
+
+    mlp_apply        <- Nerf.forward            (utils/nets.py:34-43, utils/xyz.py:16-36)
+    composite_apply  <- volume_render           (utils/rendering.py:47-85)
+    stratified_ts    <- the sampler lines       (utils/rendering.py:24-30)
+    generate_rays    <- rays_single_cam + pose  (utils/xyz.py:38-52, utils/rendering.py:129-134)
+
+Everything here requires CUDA tensors; there is no eager/PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, config
+
+NUM_PARAMS = 595844
+_PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16}
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------- weights
+class PackedWeights:
+    """Kernel-format copy of the 24 parameters (bf16 tcgen05 operand images), refreshed whenever
+    a parameter's version counter or storage changes (the caller's optimizer updates the fp32
+    masters in place between calls, train.py:55)."""
+
+    def __init__(self):
+        self.buf = None
+        self.key = None
+
+    def get(self, params, precision):
+        if precision == _lib.FP32:
+            return None
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self.buf is None or self.key != key or self.buf.device != params[0].device:
+            lib = _lib.load()
+            nbytes = lib.nb200_packed_weights_bytes(precision)
+            if self.buf is None or self.buf.device != params[0].device:
+                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+            rc = lib.nb200_pack_weights(precision, _lib.ptr_array(params), _lib.ptr(self.buf),
+                                        _lib.stream_ptr(params[0].device))
+            _lib.check(rc, "nb200_pack_weights")
+            self.key = key
+        return self.buf
+
+
+class _MLPFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, precision, in_mode, N, need_grad, packed, in0, in1, *params):
+        lib = _lib.load()
+        dev = in0.device
+        M = in0.shape[0] if in_mode == _lib.IN_POINTS else in0.shape[0] * N
+        out = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        saved = None
+        if need_grad:
+            saved = torch.empty(lib.nb200_mlp_saved_bytes(precision, M), dtype=torch.uint8, device=dev)
+        sb = lib.nb200_mlp_scratch_bytes(precision, M, 0) if not need_grad or precision == _lib.BF16 else 0
+        scratch = torch.empty(sb, dtype=torch.uint8, device=dev) if sb else None
+        rc = lib.nb200_mlp_forward(precision, in_mode, _lib.ptr(in0), _lib.ptr(in1), M, N,
+                                   _lib.ptr_array(params), _lib.ptr(packed), _lib.ptr(out),
+                                   _lib.ptr(saved), _lib.ptr(scratch), sb, _lib.stream_ptr(dev))
+        _lib.check(rc, "nb200_mlp_forward")
+        if need_grad:
+            ctx.meta = (precision, in_mode, N, M)
+            ctx.packed = packed
+            ctx.aux = (in0, in1, saved)
+            ctx.save_for_backward(*params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        precision, in_mode, N, M = ctx.meta
+        in0, in1, saved = ctx.aux
+        params = ctx.saved_tensors
+        dev = d_out.device
+        d_out = _f32c(d_out, "d_out")
+        flat = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for p in params:
+            n = p.numel()
+            views.append(flat[off:off + n].view(p.shape))
+            off += n
+        sb = lib.nb200_mlp_scratch_bytes(precision, M, 1)
+        scratch = torch.empty(sb, dtype=torch.uint8, device=dev) if sb else None
+        rc = lib.nb200_mlp_backward(precision, in_mode, _lib.ptr(in0), _lib.ptr(in1), M, N,
+                                    _lib.ptr_array(params), _lib.ptr(ctx.packed), _lib.ptr(d_out),
+                                    _lib.ptr(saved), _lib.ptr_array(views), _lib.ptr(scratch), sb,
+                                    _lib.stream_ptr(dev))
+        _lib.check(rc, "nb200_mlp_backward")
+        return (None, None, None, None, None, None, None) + tuple(views)
+
+
+def mlp_apply(net, in_mode, in0, in1=None, N=1, precision=None):
+    """Run the fused posenc+MLP for `net` (a nerf_simple_b200.nets.Nerf).  Returns [M,4]."""
+    precision = _PREC[precision or getattr(net, "precision", None) or config.get_precision()]
+    params = net.kernel_params()
+    _lib.require_cuda(params[0], "Nerf parameters (call net.cuda())")
+    in0 = _f32c(in0, "input")
+    if in_mode == _lib.IN_RAYS:
+        in1 = _f32c(in1, "ts")
+    packed = net._packed.get(params, precision)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    cap = config._state["max_samples_per_call"]
+    M = in0.shape[0] if in_mode == _lib.IN_POINTS else in0.shape[0] * N
+    if need_grad or M <= cap or precision == _lib.BF16:
+        return _MLPFunction.apply(precision, in_mode, N, need_grad, packed, in0, in1, *params)
+    # inference in fp32 parity mode: bound the per-call activation workspace
+    step = max(1, cap // N) if in_mode == _lib.IN_RAYS else cap
+    outs = []
+    for s in range(0, in0.shape[0], step):
+        a = in0[s:s + step]
+        b = in1[s:s + step] if in1 is not None else None
+        outs.append(_MLPFunction.apply(precision, in_mode, N, False, packed, a, b, *params))
+    return torch.cat(outs)
+
+
+# ---------------------------------------------------------------------------- compositing
+class _CompositeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outs, ts, dirs, dirs_mode, want_aw):
+        lib = _lib.load()
+        B, N = ts.shape
+        dev = outs.device
+        rgb = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        disp = torch.empty((B,), dtype=torch.float32, device=dev)
+        acc = torch.empty((B,), dtype=torch.float32, device=dev)
+        alpha = torch.empty((B, N), dtype=torch.float32, device=dev) if want_aw else None
+        w = torch.empty((B, N), dtype=torch.float32, device=dev) if want_aw else None
+        rc = lib.nb200_composite_forward(_lib.ptr(outs), _lib.ptr(ts), _lib.ptr(dirs), dirs_mode, B, N,
+                                         _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), _lib.ptr(alpha),
+                                         _lib.ptr(w), _lib.stream_ptr(dev))
+        _lib.check(rc, "nb200_composite_forward")
+        ctx.dirs_mode = dirs_mode
+        ctx.save_for_backward(outs, ts, dirs)
+        ctx.set_materialize_grads(False)
+        if want_aw:
+            return rgb, disp, alpha, acc, w
+        return rgb, disp, acc
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_disp, *rest):
+        lib = _lib.load()
+        outs, ts, dirs = ctx.saved_tensors
+        if len(rest) == 3:
+            d_alpha, d_acc, d_w = rest
+        else:
+            (d_acc,), d_alpha, d_w = rest, None, None
+        B, N = ts.shape
+        dev = outs.device
+        prep = lambda g: None if g is None else _f32c(g, "cotangent")
+        d_rgb = torch.zeros((B, 3), dtype=torch.float32, device=dev) if d_rgb is None else prep(d_rgb)
+        d_disp, d_alpha, d_acc, d_w = prep(d_disp), prep(d_alpha), prep(d_acc), prep(d_w)
+        d_outs = torch.empty_like(outs)
+        rc = lib.nb200_composite_backward(_lib.ptr(outs), _lib.ptr(ts), _lib.ptr(dirs), ctx.dirs_mode,
+                                          _lib.ptr(d_rgb), _lib.ptr(d_disp), _lib.ptr(d_acc),
+                                          _lib.ptr(d_alpha), _lib.ptr(d_w), B, N, _lib.ptr(d_outs),
+                                          _lib.stream_ptr(dev))
+        _lib.check(rc, "nb200_composite_backward")
+        return d_outs, None, None, None, None
+
+
+def composite_apply(outs, ts, dirs, dirs_mode=0, want_alpha_weights=True):
+    outs = _f32c(outs, "nerf_outs")
+    ts = _f32c(ts, "ts")
+    dirs = _f32c(dirs, "dirs")
+    B, N = ts.shape
+    if outs.shape != (B, N, 4):
+        raise ValueError(f"nerf_outs must be [B,N,4]; got {tuple(outs.shape)} for ts {tuple(ts.shape)}")
+    if N < 2:
+        raise ValueError("compositing needs N >= 2 samples per ray (the reference degenerates at N=1)")
+    if dirs.shape != (B, 6 if dirs_mode else 3):
+        raise ValueError(f"dirs has shape {tuple(dirs.shape)}")
+    return _CompositeFunction.apply(outs, ts, dirs, dirs_mode, want_alpha_weights)
+
+
+# -------------------------------------------------------------------------------- sampler
+def stratified_ts(B, N, tn=2.0, tf=6.0, u=None, device=None, seed=None, offset=None):
+    """ts[B,N].  u given -> reference-RNG mode (bit-identical to utils/rendering.py:25-29);
+    otherwise device Philox keyed by (seed, offset)."""
+    lib = _lib.load()
+    if u is not None:
+        u = _f32c(u, "u")
+        device = u.device
+    ts = torch.empty((B, N), dtype=torch.float32, device=device)
+    if u is None and seed is None:
+        seed, offset = config.next_philox(B * N)
+    rc = lib.nb200_stratified_ts(_lib.ptr(u), int(seed or 0), int(offset or 0), B, N, float(tn), float(tf),
+                                 _lib.ptr(ts), _lib.stream_ptr(ts.device))
+    _lib.check(rc, "nb200_stratified_ts")
+    return ts
+
+
+# --------------------------------------------------------------------------------- raygen
+def generate_rays(poses, H, W, f, ray_begin=0, n_rays=None):
+    """rays[n,6] on the device of `poses` ([P,4,4] or [4,4] camera-to-world, CUDA)."""
+    lib = _lib.load()
+    poses = _f32c(poses, "poses")
+    if poses.dim() == 2:
+        poses = poses[None]
+    P = poses.shape[0]
+    if n_rays is None:
+        n_rays = P * H * W - ray_begin
+    rays = torch.empty((n_rays, 6), dtype=torch.float32, device=poses.device)
+    rc = lib.nb200_generate_rays(_lib.ptr(poses), P, int(H), int(W), float(f), int(ray_begin), int(n_rays),
+                                 _lib.ptr(rays), _lib.stream_ptr(poses.device))
+    _lib.check(rc, "nb200_generate_rays")
+    return rays
+
+
+def positional_encoding(v, Lp=10, Ld=4):
+    lib = _lib.load()
+    v = _f32c(v, "vec")
+    M = v.shape[0]
+    posx = torch.empty((M, 3 + 6 * Lp), dtype=torch.float32, device=v.device)
+    posd = torch.empty((M, 3 + 6 * Ld), dtype=torch.float32, device=v.device)
+    rc = lib.nb200_positional_encoding(_lib.ptr(v), M, Lp, Ld, _lib.ptr(posx), _lib.ptr(posd),
+                                       _lib.stream_ptr(v.device))
+    _lib.check(rc, "nb200_positional_encoding")
+    return posx, posd

@@ -1,0 +1,257 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python host layer) against the
+numpy oracle and the reference-generated golden vectors.  Run on the B200 box with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}        # BASELINE.json north_star tolerances (max abs err)
+
+
+def maxabs(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+
+
+@pytest.fixture(scope="module")
+def net(golden_weights):
+    from nerf_simple_b200.nets import Nerf
+    n = Nerf().cuda()
+    n.load_state_dict({k: torch.from_numpy(v) for k, v in golden_weights.items()}, strict=True)
+    return n
+
+
+@pytest.fixture(params=["fp32", "bf16"])
+def precision(request):
+    from nerf_simple_b200 import config
+    config.set_precision(request.param)
+    config.set_sampler("reference")
+    yield request.param
+    config.set_precision("bf16")
+
+
+def test_library_targets_sm100():
+    from nerf_simple_b200 import _lib
+    lib = _lib.load()
+    assert lib.nb200_compiled_arch() == 100
+    assert lib.nb200_device_arch() // 10 == 10, "tests must run on a B200 (sm_100)"
+
+
+def test_raygen_matches_reference():
+    from nerf_simple_b200 import ops
+    from nerf_simple_b200.xyz import rays_single_cam
+    g = load_golden("case_raygen.npz")
+    for tag in ("h5w7", "h100", "h6w4"):
+        H, W, f = g[f"{tag}.cam"]
+        dirs = rays_single_cam([int(H), int(W), float(f)])
+        assert np.array_equal(dirs.numpy(), g[f"{tag}.dirs"])               # bit exact
+        rays = ops.generate_rays(torch.from_numpy(g[f"{tag}.poses"]).cuda(), int(H), int(W), float(f))
+        assert maxabs(rays, g[f"{tag}.rays"]) <= 1e-6
+        # sub-range == slice of the full table (sharded render relies on it)
+        part = ops.generate_rays(torch.from_numpy(g[f"{tag}.poses"]).cuda(), int(H), int(W), float(f),
+                                 ray_begin=7, n_rays=11)
+        assert torch.equal(part, rays[7:18])
+
+
+def test_sampler_bit_exact_and_philox():
+    from nerf_simple_b200 import ops
+    g = load_golden("case_train_b64_n64.npz")
+    ts = ops.stratified_ts(64, 64, 2, 6, u=torch.from_numpy(g["u"]).cuda())
+    assert np.array_equal(ts.cpu().numpy(), g["ts"])
+    for N in (7, 100, 128):
+        u = torch.rand(33, N)
+        ts = ops.stratified_ts(33, N, 2, 6, u=u.cuda())
+        assert np.array_equal(ts.cpu().numpy(), O.stratified_ts(u.numpy(), N))
+    # Philox mode: stratified (one sample per bin), deterministic in (seed, offset), uniform
+    a = ops.stratified_ts(4096, 64, 2, 6, device="cuda", seed=5, offset=0)
+    b = ops.stratified_ts(4096, 64, 2, 6, device="cuda", seed=5, offset=0)
+    c = ops.stratified_ts(4096, 64, 2, 6, device="cuda", seed=6, offset=0)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    bins = torch.linspace(2, 6, 65, device="cuda")
+    assert bool(((a >= bins[:-1]) & (a <= bins[1:])).all())
+    frac = (a - bins[:-1]) / (4 / 64)
+    assert abs(float(frac.mean()) - 0.5) < 5e-3 and abs(float(frac.var()) - 1 / 12) < 5e-3
+
+
+def test_posenc_matches_reference():
+    from nerf_simple_b200.xyz import positional_encoder, gamma
+    g = load_golden("case_train_b64_n64.npz")
+    q = torch.from_numpy(g["query"][:256]).cuda()
+    posx, posd = positional_encoder(q)
+    assert posx.shape == (256, 63) and posd.shape == (256, 27)
+    assert maxabs(posx, g["posx"]) <= 2e-6 and maxabs(posd, g["posd"]) <= 2e-6
+    gx = gamma(q[:, 0:1], 10)
+    assert maxabs(gx, g["posx"][:, 3:23]) <= 2e-6
+
+
+@pytest.mark.parametrize("tag", ["n40", "n64", "n128", "n192", "n2", "n7"])
+def test_compositing_isolated(tag):
+    from nerf_simple_b200.rendering import volume_render
+    g = load_golden("case_composite.npz")
+    G = lambda k: torch.from_numpy(g[f"{tag}.{k}"]).cuda()
+    outs = G("outs").requires_grad_(True)
+    rgb, disp, alpha, acc, w = volume_render(outs, G("ts"), G("dirs"))
+    assert maxabs(rgb, G("rgb")) <= 2e-6
+    assert maxabs(alpha, G("alpha")) <= 1e-6
+    assert maxabs(w, G("w")) <= 1e-6
+    assert maxabs(acc, G("acc")) <= 2e-6
+    assert float(((disp - G("disp")).abs() / G("disp").abs()).max()) <= 1e-5
+    tot = (rgb * G("c_rgb")).sum() + (disp * G("c_disp")).sum() + (alpha * G("c_alpha")).sum() \
+        + (acc * G("c_acc")).sum() + (w * G("c_w")).sum()
+    tot.backward()
+    ref = g[f"{tag}.d_outs"]
+    assert maxabs(outs.grad, ref) <= 2e-4 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_compositing_long_ray_fallback():
+    """N > 256 takes the thread-per-ray kernels; check against the oracle."""
+    from nerf_simple_b200.rendering import volume_render
+    rng = np.random.default_rng(3)
+    B, N = 37, 300
+    outs = rng.standard_normal((B, N, 4)).astype(np.float32)
+    ts = np.sort(2 + 4 * rng.random((B, N)), axis=1).astype(np.float32)
+    dirs = rng.standard_normal((B, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    c_rgb = rng.standard_normal((B, 3)).astype(np.float32)
+    o = torch.from_numpy(outs).cuda().requires_grad_(True)
+    rgb, disp, alpha, acc, w = volume_render(o, torch.from_numpy(ts).cuda(), torch.from_numpy(dirs).cuda())
+    r_rgb, r_disp, r_alpha, r_acc, r_w = O.volume_render(outs, ts, dirs)
+    assert maxabs(rgb, r_rgb) <= 5e-6 and maxabs(w, r_w) <= 2e-6 and maxabs(alpha, r_alpha) <= 2e-6
+    (rgb * torch.from_numpy(c_rgb).cuda()).sum().backward()
+    ref = O.volume_render_backward(outs, ts, dirs, c_rgb)
+    assert maxabs(o.grad, ref) <= 2e-4 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_mlp_forward_points(net, precision, golden_weights):
+    g = load_golden("case_train_b64_n64.npz")
+    with torch.no_grad():
+        out = net(torch.from_numpy(g["query"]).cuda())
+    assert out.shape == (4096, 4)
+    assert maxabs(out, g["out"]) <= TOL[precision]
+    # ragged M (not a multiple of any tile size)
+    with torch.no_grad():
+        out = net(torch.from_numpy(g["query"][:1000 + 37]).cuda())
+    assert maxabs(out, g["out"][:1037]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("case,N", [("case_train_b64_n64.npz", 64), ("case_render_b1024_n64.npz", 64),
+                                    ("case_all5_b96_n128.npz", 128)])
+def test_render_nerf_forward(net, precision, case, N):
+    from nerf_simple_b200.rendering import render_nerf
+    g = load_golden(case)
+    torch.manual_seed(0)
+    # inject the golden jitter through the reference-RNG path: render_nerf draws torch.rand(B,N)
+    # from the CPU generator, so re-seed to the value the golden generator used
+    seed = {"case_train_b64_n64.npz": 1, "case_render_b1024_n64.npz": 11, "case_all5_b96_n128.npz": 5}[case]
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        rgb, disp, alpha, acc, w = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, N)
+    tol = TOL[precision]
+    assert maxabs(rgb, g["rgb"]) <= tol
+    assert maxabs(alpha, g["alpha"]) <= tol
+    assert maxabs(w, g["weights"]) <= tol
+    assert maxabs(acc, g["acc"]) <= tol
+    assert float(((disp - torch.from_numpy(g["disp"]).cuda()).abs() / torch.from_numpy(g["disp"]).cuda().abs()).max()) <= 10 * tol
+    if precision == "bf16":
+        mse = float(((rgb.cpu() - torch.from_numpy(g["rgb"])) ** 2).mean())
+        assert 10 * np.log10(1.0 / max(mse, 1e-20)) > 60          # PSNR of our render vs the reference's
+
+
+def _grad_check(net, grads_ref, rtol):
+    for k, p in net.named_parameters():
+        ref = grads_ref[k]
+        scale = max(1e-6, float(np.max(np.abs(ref))))
+        assert maxabs(p.grad, ref) <= rtol * scale, k
+
+
+def test_train_step_gradients(net, precision):
+    """train.py:51-54: MSE loss through rgb only; all 24 gradients vs the reference's autograd."""
+    from nerf_simple_b200.rendering import render_nerf
+    g = load_golden("case_train_b64_n64.npz")
+    net.zero_grad()
+    torch.manual_seed(1)
+    rgb, *_ = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 64)
+    loss = torch.nn.MSELoss()(rgb, torch.from_numpy(g["gt"]).cuda())
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= (1e-5 if precision == "fp32" else 2e-3)
+    _grad_check(net, {k[5:]: v for k, v in g.items() if k.startswith("grad.")},
+                2e-3 if precision == "fp32" else 5e-2)
+    # gradients accumulate across backward calls like autograd
+    g1 = [p.grad.clone() for p in net.parameters()]
+    torch.manual_seed(1)
+    rgb, *_ = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 64)
+    torch.nn.MSELoss()(rgb, torch.from_numpy(g["gt"]).cuda()).backward()
+    for a, p in zip(g1, net.parameters()):
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-3 if precision == "fp32" else 5e-2, atol=1e-7)
+
+
+def test_all_five_outputs_gradient(net, precision):
+    from nerf_simple_b200.rendering import render_nerf
+    g = load_golden("case_all5_b96_n128.npz")
+    net.zero_grad()
+    torch.manual_seed(5)
+    o5 = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 128)
+    cot = [g["cot_rgb"], g["cot_disp"], g["cot_alpha"], g["cot_acc"], g["cot_w"]]
+    sum((a * torch.from_numpy(b).cuda()).sum() for a, b in zip(o5, cot)).backward()
+    grads = {k[5:]: v for k, v in g.items() if k.startswith("grad.")}
+    for k, p in net.named_parameters():
+        if k in grads:
+            scale = max(1e-6, float(np.abs(grads[k]).max()))
+            # conditioning of this case is ~1.2e-2 (see tests/test_oracle.py)
+            assert maxabs(p.grad, grads[k]) <= (3e-2 if precision == "fp32" else 1e-1) * scale, k
+
+
+def test_full_size_properties(net, precision):
+    """BASELINE sizes (4096 rays x 64): properties that need no oracle run."""
+    from nerf_simple_b200 import ops, config
+    from nerf_simple_b200.rendering import render_nerf
+    poses = torch.stack(__import__("nerf_simple_b200.xyz", fromlist=["x"]).poses_to_render(4, -30, 3)).cuda()
+    f = 800 / (2 * np.tan(0.6911112070083618 / 2))
+    rays = ops.generate_rays(poses, 800, 800, f, ray_begin=800 * 800 + 123456, n_rays=4096)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        rgb, disp, alpha, acc, w = render_nerf(rays, net, 64)
+    assert rgb.shape == (4096, 3) and alpha.shape == (4096, 64)
+    assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(disp).all())
+    # last delta is 1e10 => alpha_last == 1 and the weights sum to 1
+    assert float((acc - 1).abs().max()) <= 1e-4
+    assert float((w.sum(1) - acc).abs().max()) <= 1e-5
+    # chunk independence: rendering a sub-batch with the same jitter gives the same pixels
+    torch.manual_seed(3)
+    u = torch.rand(4096, 64)
+    ts = ops.stratified_ts(4096, 64, 2, 6, u=u.cuda())
+    from nerf_simple_b200 import _lib
+    with torch.no_grad():
+        full = ops.mlp_apply(net, _lib.IN_RAYS, rays, ts, 64)
+        part = ops.mlp_apply(net, _lib.IN_RAYS, rays[1000:1500], ts[1000:1500], 64)
+    assert maxabs(full.view(4096, 64, 4)[1000:1500].reshape(-1, 4), part) <= (1e-6 if precision == "fp32" else 1e-6)
+
+
+def test_render_image_and_poses_shapes(net, precision, tmp_path):
+    """Host drivers (utils/rendering.py:88-160) incl. the remainder chunk the reference drops."""
+    from nerf_simple_b200 import ops
+    from nerf_simple_b200.rendering import render_image, render_poses
+    from nerf_simple_b200.xyz import poses_to_render
+    H = W = 20
+    f = W / (2 * np.tan(0.6911112070083618 / 2))
+    poses = poses_to_render(4, -30, 2)
+
+    class RG:                                   # minimal stand-in for RayGenerator
+        samples = {"val": [{"img": np.zeros((H, W, 3))}]}
+        rays_dataset = {"val": ops.generate_rays(torch.stack(poses).cuda(), H, W, f).cpu()}
+    rgb, depth, gt = render_image(net, RG, batch_size=150, im_idx=0, im_set="val")   # 400 = 2*150 + 100
+    assert rgb.shape == (1, H, W, 3) and depth.shape == (1, H, W, 1) and gt.shape == (1, H, W, 3)
+    assert float(rgb.min()) >= 0 and float(rgb.max()) <= 1 and not rgb.is_cuda
+    frames = render_poses(net, poses, [H, W, f], 128, savepath=str(tmp_path))
+    assert len(frames) == 2 and frames[0].shape == (H, W, 3)
+
+
+def test_cpu_tensor_fails_loudly(net):
+    from nerf_simple_b200._lib import NerfB200Error
+    with pytest.raises(NerfB200Error):
+        net(torch.zeros(4, 6))
