@@ -24,6 +24,12 @@ int record_cuda_error(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::nb200::record_cuda_error(_e, name);            \
   } while (0)
 
+#define NB_TRY_RC(expr)                 \
+  do {                                  \
+    int _rc = (expr);                   \
+    if (_rc != NB200_OK) return _rc;    \
+  } while (0)
+
 static inline cudaStream_t as_stream(nb200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
