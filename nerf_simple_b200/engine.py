@@ -1,0 +1,81 @@
+"""Device-resident drivers of the hot path: what bench.py and the multi-GPU entry points call.
+
+`FrameRenderer` renders whole novel views (the loop of utils/rendering.py:139-151) with rays
+generated on the device, Philox jitter, the fused MLP kernel and the compositing kernel: four
+launches per frame, no per-chunk host traffic.  `shard_range` / `render_sharded` split the rays
+of a frame across ranks with one final gather.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced [begin, end) range of `n_items` for `rank` of `world`."""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class FrameRenderer:
+    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None):
+        self.net, self.H, self.W, self.f, self.N = net, int(H), int(W), float(f), int(N)
+        self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
+        self.precision = precision
+        self.device = next(net.parameters()).device
+        self._offset = 0
+        self.launches = 0          # kernels of libnerf_b200 launched so far
+        self.mlp_events = []       # optional (start, stop) CUDA events around the MLP kernel
+
+    def render_rays(self, poses_dev, ray_begin, n_rays, time_mlp=False):
+        """rgb [n,3] clipped to [0,1] and disparity [n] for rays [ray_begin, ray_begin+n) of the
+        pose table `poses_dev` ([P,4,4] on the device)."""
+        with torch.no_grad():
+            rays = ops.generate_rays(poses_dev, self.H, self.W, self.f, ray_begin, n_rays)
+            ts = ops.stratified_ts(n_rays, self.N, self.tn, self.tf, device=self.device, seed=self.seed,
+                                   offset=self._offset)
+            self._offset += (n_rays * self.N + 3) // 4
+            if time_mlp:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            out = ops.mlp_apply(self.net, _lib.IN_RAYS, rays, ts, self.N, precision=self.precision)
+            if time_mlp:
+                e1.record()
+                self.mlp_events.append((e0, e1))
+            rgb, disp, _ = ops.composite_apply(out.view(n_rays, self.N, 4), ts, rays, dirs_mode=1,
+                                               want_alpha_weights=False)
+            self.launches += 4
+            return rgb.clamp_(0.0, 1.0), disp
+
+    def render_frame(self, poses_dev, idx=0, time_mlp=False):
+        n = self.H * self.W
+        rgb, disp = self.render_rays(poses_dev, idx * n, n, time_mlp)
+        return rgb.view(self.H, self.W, 3), disp.view(self.H, self.W)
+
+    def render_frame_host(self, pose_cpu_pinned, out_rgb_pinned, out_disp_pinned):
+        """End-to-end call with HOST buffers: pose (pinned, [4,4]) in, frame out (pinned)."""
+        pose = pose_cpu_pinned.to(self.device, non_blocking=True).view(1, 4, 4)
+        rgb, disp = self.render_frame(pose, 0)
+        out_rgb_pinned.copy_(rgb, non_blocking=True)
+        out_disp_pinned.copy_(disp, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_rgb_pinned, out_disp_pinned
+
+
+def render_sharded(renderer: FrameRenderer, poses_dev, idx, rank, world, gather=True):
+    """Ray-sharded render of frame `idx`: each rank renders a contiguous band of rays; one
+    all_gather of (rgb, disp) = 16 B/ray assembles the frame on every rank."""
+    import torch.distributed as dist
+    n = renderer.H * renderer.W
+    b, e = shard_range(n, rank, world)
+    rgb, disp = renderer.render_rays(poses_dev, idx * n + b, e - b)
+    if not gather or world == 1:
+        return rgb, disp
+    packed = torch.cat([rgb, disp[:, None]], dim=1)                  # [n_local, 4]
+    sizes = [shard_range(n, r, world) for r in range(world)]
+    parts = [torch.empty((e2 - b2, 4), dtype=packed.dtype, device=packed.device) for b2, e2 in sizes]
+    dist.all_gather(parts, packed)
+    full = torch.cat(parts)
+    return full[:, :3].reshape(renderer.H, renderer.W, 3), full[:, 3].reshape(renderer.H, renderer.W)
