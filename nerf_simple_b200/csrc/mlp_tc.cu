@@ -39,12 +39,14 @@ struct SlabDesc {
   uint8_t ksteps;   // number of K=16 MMAs
   uint8_t first;    // first slab of its layer (accumulator is overwritten)
   uint8_t last;     // last slab of its layer (commit to acc_full)
-  uint8_t pad;
+  uint8_t transposed;  // image(n,k) = W[(wcol0+k)*ldw + n] (dgrad operand) instead of W[n*ldw + wcol0+k]
 };
 
 struct PackedLayout {
   int num_fwd;
   SlabDesc fwd[kMaxSlabs];
+  int num_bwd;
+  SlabDesc bwd[kMaxSlabs];  // dgrad chain: transposed weight images, 9 MMA layers
   uint32_t f32_off;  // fp32 section: bias[10][256] | wsig[256] | bsig(+pad 4) | wc1[3][128] | bc1[3](+pad)
   uint32_t total_bytes;
 };
@@ -60,41 +62,60 @@ __host__ __device__ constexpr int mma_layer_of(int ml) {
 }
 
 struct LayoutBuilder {
-  PackedLayout* L;
+  SlabDesc* arr;
   uint32_t off;
   int s;
-  void add(int ml, int n, int wcol0, int kvalid, int ldw, int src, int kb, int ksteps) {
-    SlabDesc& d = L->fwd[s++];
+  void add(int ml, int layer, int transposed, int n, int wcol0, int kvalid, int ldw, int src, int kb, int ksteps) {
+    SlabDesc& d = arr[s++];
     d.off = off; d.bytes = (uint32_t)n * 128u; d.n = (uint16_t)n; d.wcol0 = (uint16_t)wcol0;
-    d.kvalid = (uint16_t)kvalid; d.ldw = (uint16_t)ldw; d.ml = (uint8_t)ml; d.layer = (uint8_t)mma_layer_of(ml);
+    d.kvalid = (uint16_t)kvalid; d.ldw = (uint16_t)ldw; d.ml = (uint8_t)ml; d.layer = (uint8_t)layer;
     d.src = (uint8_t)src; d.kb = (uint8_t)kb; d.ksteps = (uint8_t)ksteps; d.first = 0; d.last = 0;
+    d.transposed = (uint8_t)transposed;
     off += d.bytes;
   }
 };
 
+// dgrad chain (mlp_bwd.cuh): MMA layer bl = 1..9 computes delta_in = delta_out @ W (W un-transposed
+// [out,in]); its B operand image is W^T: image(n = in-feature, k = out-feature).
+__host__ __device__ constexpr int bwd_layer_of(int bl) {
+  return bl == 1 ? L_C0 : (bl == 2 ? L_2 : (bl == 3 ? L1_1 : (bl == 4 ? L1_0 : (bl == 5 ? L_SKIP : L0_4 - (bl - 6)))));
+}
+
 static void build_layout() {
   memset(&h_layout, 0, sizeof(h_layout));
   LayoutBuilder b;
-  b.L = &h_layout; b.off = 0; b.s = 0;
+  b.arr = h_layout.fwd; b.off = 0; b.s = 0;
   for (int ml = 0; ml < kNumMmaLayers; ++ml) {
-    const int first = b.s;
+    const int first = b.s, ly = mma_layer_of(ml);
     if (ml == 0) {
-      b.add(ml, 256, 0, kPosX, kPosX, 1, 0, 4);
+      b.add(ml, ly, 0, 256, 0, kPosX, kPosX, 1, 0, 4);
     } else if (ml == 5) {  // cat([h, posx]) (utils/nets.py:38)
-      for (int kb = 0; kb < 4; ++kb) b.add(ml, 256, kb * 64, 64, kHidden + kPosX, 0, kb, 4);
-      b.add(ml, 256, 256, kPosX, kHidden + kPosX, 1, 0, 4);
+      for (int kb = 0; kb < 4; ++kb) b.add(ml, ly, 0, 256, kb * 64, 64, kHidden + kPosX, 0, kb, 4);
+      b.add(ml, ly, 0, 256, 256, kPosX, kHidden + kPosX, 1, 0, 4);
     } else if (ml == 9) {  // cat([g, posd]) (utils/nets.py:42), 128 outputs
-      for (int kb = 0; kb < 4; ++kb) b.add(ml, 128, kb * 64, 64, kHidden + kPosD, 0, kb, 4);
-      b.add(ml, 128, 256, kPosD, kHidden + kPosD, 1, 0, 2);
+      for (int kb = 0; kb < 4; ++kb) b.add(ml, ly, 0, 128, kb * 64, 64, kHidden + kPosD, 0, kb, 4);
+      b.add(ml, ly, 0, 128, 256, kPosD, kHidden + kPosD, 1, 0, 2);
     } else {
-      for (int kb = 0; kb < 4; ++kb) b.add(ml, 256, kb * 64, 64, kHidden, 0, kb, 4);
+      for (int kb = 0; kb < 4; ++kb) b.add(ml, ly, 0, 256, kb * 64, 64, kHidden, 0, kb, 4);
     }
     h_layout.fwd[first].first = 1;
     h_layout.fwd[b.s - 1].last = 1;
   }
   h_layout.num_fwd = b.s;
-  h_layout.f32_off = b.off;
-  h_layout.total_bytes = b.off + kF32Floats * (uint32_t)sizeof(float);
+  // dgrad slabs: n = 256 input features (rows of the image), k-blocks over the output features
+  LayoutBuilder t;
+  t.arr = h_layout.bwd; t.off = b.off; t.s = 0;
+  for (int bl = 1; bl <= 9; ++bl) {
+    const int first = t.s, ly = bwd_layer_of(bl);
+    const int ldw = (ly == L_C0) ? kHidden + kPosD : (ly == L_SKIP ? kHidden + kPosX : kHidden);
+    const int nkb = (bl == 1) ? 2 : 4;  // color_fc.0 has 128 outputs
+    for (int kb = 0; kb < nkb; ++kb) t.add(bl, ly, 1, 256, kb * 64, 64, ldw, 0, kb, 4);
+    h_layout.bwd[first].first = 1;
+    h_layout.bwd[t.s - 1].last = 1;
+  }
+  h_layout.num_bwd = t.s;
+  h_layout.f32_off = t.off;
+  h_layout.total_bytes = t.off + kF32Floats * (uint32_t)sizeof(float);
 }
 
 static int ensure_layout() {
@@ -107,19 +128,25 @@ static int ensure_layout() {
 
 struct ParamPtrs { const float* p[24]; };
 
-// One block per slab: fp32 weight [n x ldw] columns [wcol0, wcol0+64) -> bf16 SWIZZLE_128B image.
+// One block per slab: fp32 weight -> bf16 SWIZZLE_128B operand image [n rows x 64 k-columns].
 __global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
-  const SlabDesc d = c_layout.fwd[blockIdx.x];
+  const bool is_bwd = (int)blockIdx.x >= c_layout.num_fwd;
+  const SlabDesc d = is_bwd ? c_layout.bwd[blockIdx.x - c_layout.num_fwd] : c_layout.fwd[blockIdx.x];
   const float* W = P.p[2 * d.layer];
   for (int item = threadIdx.x; item < d.n * 8; item += blockDim.x) {
     const int n = item >> 3, j = item & 7;
     uint32_t w[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int k0 = j * 8 + 2 * e;
-      const float a = (k0 < d.kvalid) ? __ldg(W + (size_t)n * d.ldw + d.wcol0 + k0) : 0.f;
-      const float b = (k0 + 1 < d.kvalid) ? __ldg(W + (size_t)n * d.ldw + d.wcol0 + k0 + 1) : 0.f;
-      w[e] = pack_bf16x2(a, b);
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = j * 8 + 2 * e + h;
+        v[h] = 0.f;
+        if (k < d.kvalid)
+          v[h] = d.transposed ? __ldg(W + (size_t)(d.wcol0 + k) * d.ldw + n) : __ldg(W + (size_t)n * d.ldw + d.wcol0 + k);
+      }
+      w[e] = pack_bf16x2(v[0], v[1]);
     }
     *reinterpret_cast<uint4*>(packed + d.off + sw128_off(n, j)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -157,11 +184,16 @@ constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;  // slack for manual 1024 B 
 constexpr int kFwdThreads = 320;
 
 // saved activations (training): tensors 0..7 = h0..h7, 8 = g (256 cols, 64 KB per tile), 9 = c1
-// (128 cols, 32 KB per tile); every tile is stored as [K-block][128 rows x 128 B SWIZZLE_128B], i.e.
-// exactly the UMMA operand image the backward kernels bulk-copy back into shared memory.
-constexpr size_t kSavedTileBytes = 9 * 65536 + 32768;
+// (128 cols, 32 KB per tile), 10 = posx (64 cols, 16 KB), 11 = posd (32 of 64 cols, 16 KB).  Every
+// tile is stored as [K-block][128 rows x 128 B SWIZZLE_128B], i.e. exactly the UMMA operand image
+// the backward kernels bulk-copy back into shared memory (K-major for dgrad, MN-major for wgrad).
+constexpr size_t kSavedTileBytes = 9 * 65536 + 32768 + 16384 + 16384;
 __host__ __device__ __forceinline__ size_t saved_tensor_off(int t, int64_t num_tiles) {
-  return (size_t)t * (size_t)num_tiles * 65536;
+  const size_t per_tile = t < 9 ? (size_t)t * 65536 : (t == 9 ? 9 * 65536 : (t == 10 ? 9 * 65536 + 32768 : 9 * 65536 + 49152));
+  return per_tile * (size_t)num_tiles;
+}
+__host__ __device__ __forceinline__ size_t saved_tile_bytes(int t) {
+  return t < 9 ? 65536 : (t == 9 ? 32768 : 16384);
 }
 
 struct FwdParams {
@@ -200,7 +232,7 @@ __device__ __forceinline__ void load_query_tc(const FwdParams& p, int64_t m, flo
 // Level 0 uses the accurate sincosf; higher levels the double-angle recurrence (abs. error
 // <= 2^i * 1e-7, far below bf16 resolution).
 template <int L, int NCH>
-__device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, uint32_t r) {
+__device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, uint32_t r, uint8_t* gsave) {
   float f[NCH * 8];
 #pragma unroll
   for (int i = 0; i < NCH * 8; ++i) f[i] = 0.f;
@@ -220,9 +252,10 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
   }
 #pragma unroll
   for (int j = 0; j < NCH; ++j) {
-    st_shared_v4(img_base + sw128_off(r, j), pack_bf16x2(f[8 * j], f[8 * j + 1]),
-                 pack_bf16x2(f[8 * j + 2], f[8 * j + 3]), pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
-                 pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+    const uint32_t w0 = pack_bf16x2(f[8 * j], f[8 * j + 1]), w1 = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                   w2 = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), w3 = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    st_shared_v4(img_base + sw128_off(r, j), w0, w1, w2, w3);
+    if (gsave) *reinterpret_cast<uint4*>(gsave + sw128_off(r, j)) = make_uint4(w0, w1, w2, w3);
   }
 }
 
@@ -274,7 +307,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
       const int64_t m = row_valid ? m_raw : p.M - 1;
       float v[6];
       load_query_tc(p, m, v);
-      encode_row<kLp, 8>(v, e_img, r);  // posx -> E[slot], K = 64
+      encode_row<kLp, 8>(v, e_img, r,   // posx -> E[slot], K = 64
+                         kSave ? p.saved + saved_tensor_off(10, T) + (size_t)tile * 16384 : nullptr);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_act + 8 * slot);
@@ -286,7 +320,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
         const float* bias = f32sec + kF32Bias + ml * 256;
         if (ml == 5) {
           // posx has been consumed by the skip layer: the encoding buffer now carries posd
-          encode_row<kLd, 4>(v + 3, e_img, r);
+          encode_row<kLd, 8>(v + 3, e_img, r,   // cols 27..63 zero: wgrad reads the image with N = 64
+                             kSave ? p.saved + saved_tensor_off(11, T) + (size_t)tile * 16384 : nullptr);
         }
         if (ml < 9) {
           const bool relu = (ml != 8);  // layers_2 has no activation (utils/nets.py:28,41)
@@ -461,19 +496,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
   }
 }
 
+#include "mlp_tc_bwd.cuh"
+
 // ------------------------------------------------------------------------------ host API
 size_t tc_packed_bytes() {
   if (!h_layout_ready) build_layout();  // layout is host-computable without a device
   return h_layout.total_bytes;
 }
 size_t tc_saved_bytes(int64_t M) { return (size_t)ceil_div64(M, kTileM) * kSavedTileBytes; }
-size_t tc_scratch_bytes(int64_t, int) { return 0; }
+size_t tc_scratch_bytes(int64_t M, int train) { return train ? (size_t)ceil_div64(M, kTileM) * kDeltaTileBytes : 0; }
 
 int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s) {
   NB_TRY_RC(ensure_layout());
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = P[i];
-  pack_slabs_kernel<<<h_layout.num_fwd, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
+  pack_slabs_kernel<<<h_layout.num_fwd + h_layout.num_bwd, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
   NB_LAUNCH_CHECK("pack_slabs_kernel");
   pack_f32_kernel<<<(kF32Floats + 255) / 256, 256, 0, s>>>(
       pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + h_layout.f32_off));
@@ -515,9 +552,72 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   return NB200_OK;
 }
 
-int tc_backward(int, const float*, const float*, int64_t, int, const void*, const float*, const void*,
-                float* const*, void*, size_t, cudaStream_t) {
-  return NB200_ERR_UNSUPPORTED;
+int tc_backward(int, const float*, const float*, int64_t M, int, const void* packed, const float* d_out,
+                const void* saved, float* const* G, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  NB_TRY_RC(check_arch());
+  NB_TRY_RC(ensure_layout());
+  if (!scratch || scratch_bytes < tc_scratch_bytes(M, 1)) return NB200_ERR_WORKSPACE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemLaunch));
+    attr_set = true;
+  }
+  const int64_t T = ceil_div64(M, kTileM);
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+  uint8_t* ds = reinterpret_cast<uint8_t*>(scratch);
+  // 1. fused delta chain
+  BwdParams bp;
+  bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
+  bp.d_out = d_out; bp.dscr = ds;
+  {
+    const int64_t want = (T + 1) / 2;
+    const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
+    mlp_dgrad_tc_kernel<<<grid, kFwdThreads, kSmemLaunch, s>>>(bp);
+    NB_LAUNCH_CHECK("mlp_dgrad_tc_kernel");
+  }
+  // 2. weight gradients: (delta tensor, input tensor) pairs
+  WgradParams wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.T = T;
+  int n = 0;
+  auto item = [&](int dt, int st, int layer, int ldw, int col0, int ncols, int nrows, bool bias) {
+    WItem& w = wp.items[n++];
+    w.a_ptr = ds + delta_tensor_off(dt, T);
+    w.a_tile_bytes = dt == 0 ? 32768u : 65536u;
+    w.a_chunks = dt == 0 ? 2 : 4;
+    w.b_ptr = sv + saved_tensor_off(st, T);
+    w.b_tile_bytes = (uint32_t)saved_tile_bytes(st);
+    w.b_chunks = st >= 10 ? 1 : 4;
+    w.n_mma = st >= 10 ? 64 : 256;
+    w.dW = G[2 * layer]; w.db = bias ? G[2 * layer + 1] : nullptr;
+    w.ldw = ldw; w.col0 = col0; w.ncols = ncols; w.nrows = nrows;
+    w.cost = (w.a_chunks + w.b_chunks) * 16;
+  };
+  item(0, 8, L_C0, kHidden + kPosD, 0, kHidden, kHidden / 2, true);        // color_fc.0 <- g
+  item(0, 11, L_C0, kHidden + kPosD, kHidden, kPosD, kHidden / 2, false);  // color_fc.0 <- posd
+  item(1, 7, L_2, kHidden, 0, kHidden, kHidden, true);                      // layers_2   <- h7
+  item(2, 6, L1_1, kHidden, 0, kHidden, kHidden, true);                     // layers_1.2 <- h6
+  item(3, 5, L1_0, kHidden, 0, kHidden, kHidden, true);                     // layers_1.0 <- h5
+  item(4, 4, L_SKIP, kHidden + kPosX, 0, kHidden, kHidden, true);           // skip       <- h4
+  item(4, 10, L_SKIP, kHidden + kPosX, kHidden, kPosX, kHidden, false);     // skip       <- posx
+  item(5, 3, L0_4, kHidden, 0, kHidden, kHidden, true);                     // layers_0.8 <- h3
+  item(6, 2, L0_3, kHidden, 0, kHidden, kHidden, true);
+  item(7, 1, L0_2, kHidden, 0, kHidden, kHidden, true);
+  item(8, 0, L0_1, kHidden, 0, kHidden, kHidden, true);
+  item(9, 10, L0_0, kPosX, 0, kPosX, kHidden, true);                        // layers_0.0 <- posx
+  wp.num_items = n;
+  mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
+  NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");
+  // 3. sigma / colour heads
+  {
+    const int64_t blocks = T < (int64_t)sm_count() * 4 ? T : (int64_t)sm_count() * 4;
+    const int64_t tpb = ceil_div64(T, blocks);
+    mlp_head_grads_kernel<<<(unsigned)ceil_div64(T, tpb), 256, 0, s>>>(sv, d_out, M, T, tpb, G[2 * L_SIGMA], G[2 * L_SIGMA + 1],
+                                                                    G[2 * L_C1], G[2 * L_C1 + 1]);
+    NB_LAUNCH_CHECK("mlp_head_grads_kernel");
+  }
+  return NB200_OK;
 }
 
 }  // namespace nb200

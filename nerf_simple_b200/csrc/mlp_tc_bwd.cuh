@@ -1,0 +1,466 @@
+// Backward of the fused MLP on tcgen05 (included inside namespace nb200 by mlp_tc.cu).
+//
+//   mlp_dgrad_tc_kernel : fused delta chain.  Same ping-pong structure as the forward kernel; per
+//       128-sample tile it walks color_fc.0 -> layers_2 -> layers_1 -> skip -> layers_0 backwards,
+//       delta_in = (delta_out @ W) * relu'(saved activation), each delta kept in shared memory as
+//       the A operand of the next MMA and written once to HBM (bf16 tile image) for wgrad.
+//   mlp_wgrad_tc_kernel : dW = delta^T @ activation for the 12 (delta, input) pairs.  Both operands
+//       are the saved tile images read as MN-major UMMA operands (K = samples); accumulators live in
+//       TMEM across the CTA's whole tile range, bias gradients are column sums taken from the staged
+//       delta tiles by otherwise idle warps, one atomic flush per (CTA, layer) segment.
+//   mlp_head_grads_kernel: the 256->1 sigma head and 128->3 colour head on CUDA cores.
+
+// ------------------------------------------------------------------ delta scratch layout
+// tensor 0 = delta_c1 (128 cols, 32 KB/tile); tensors 1..9 = delta_g, delta_h7, ..., delta_h0 (64 KB/tile)
+constexpr size_t kDeltaTileBytes = 32768 + 9 * 65536;
+__host__ __device__ __forceinline__ size_t delta_tensor_off(int t, int64_t num_tiles) {
+  return (t == 0 ? (size_t)0 : (size_t)32768 + (size_t)(t - 1) * 65536) * (size_t)num_tiles;
+}
+
+struct BwdParams {
+  int64_t M;
+  int64_t num_tiles;
+  const uint8_t* packed;
+  const uint8_t* saved;
+  const float* d_out;  // [M,4]
+  uint8_t* dscr;       // delta scratch
+};
+
+constexpr int kBwdWStages = 3;
+constexpr uint32_t kBwdSmemW = 2 * kABytes, kBwdSmemBar = kBwdSmemW + kBwdWStages * kWStageBytes;  // 229376
+static_assert(kBwdSmemBar == kSmemBar, "dgrad kernel reuses the forward shared-memory budget");
+
+__device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t v, uint32_t h) {
+  // zero the bf16 lanes of v where the matching bf16 lane of h is not > 0 (ReLU backward)
+  const uint32_t lo = ((int16_t)(h & 0xFFFFu) > 0) ? 0x0000FFFFu : 0u;
+  const uint32_t hi = ((int16_t)(h >> 16) > 0) ? 0xFFFF0000u : 0u;
+  return v & (lo | hi);
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp_dgrad_tc_kernel(const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kBwdSmemBar;
+  const uint32_t bar_wfull = bar_base, bar_wempty = bar_base + 24, bar_act = bar_base + 48,
+                 bar_acc = bar_base + 64, tmem_slot = bar_base + 80;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdWStages; ++i) {
+      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wempty + 8 * i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_act + 8 * s, 128);
+      mbar_init(bar_acc + 8 * s, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int64_t T = p.num_tiles, G = gridDim.x;
+  const int64_t my_tiles = (blockIdx.x < T) ? (T - blockIdx.x + G - 1) / G : 0;
+  const float* f32sec = reinterpret_cast<const float*>(p.packed + c_layout.f32_off);
+
+  if (warp < 8) {
+    const int slot = warp >> 2;
+    const uint32_t r = threadIdx.x & 127;
+    const uint32_t a_img = smem_base + kSmemA + slot * kABytes;
+    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
+    uint32_t acc_parity = 0;
+    for (int64_t k = slot; k < my_tiles; k += 2) {
+      const int64_t tile = blockIdx.x + k * G;
+      const int64_t m_raw = tile * kTileM + r;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M carry zero gradient
+      if (m_raw < p.M) g = __ldg(reinterpret_cast<const float4*>(p.d_out) + m_raw);
+      {
+        // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
+        const uint8_t* c1img = p.saved + saved_tensor_off(9, T) + (size_t)tile * 32768;
+        uint8_t* dsave = p.dscr + delta_tensor_off(0, T) + (size_t)tile * 32768;
+        const float* wc1 = f32sec + kF32WC1;
+#pragma unroll 1
+        for (int q = 0; q < 16; ++q) {
+          const uint32_t o = (uint32_t)(q >> 3) * 16384u + sw128_off(r, q & 7);
+          const uint4 cm = __ldg(reinterpret_cast<const uint4*>(c1img + o));
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; e += 4) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc1 + q * 8 + e));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc1 + 128 + q * 8 + e));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(wc1 + 256 + q * 8 + e));
+            x[e] = fmaf(g.z, w2.x, fmaf(g.y, w1.x, g.x * w0.x));
+            x[e + 1] = fmaf(g.z, w2.y, fmaf(g.y, w1.y, g.x * w0.y));
+            x[e + 2] = fmaf(g.z, w2.z, fmaf(g.y, w1.z, g.x * w0.z));
+            x[e + 3] = fmaf(g.z, w2.w, fmaf(g.y, w1.w, g.x * w0.w));
+          }
+          const uint32_t w0 = mask_pos_bf16x2(pack_bf16x2(x[0], x[1]), cm.x), w1 = mask_pos_bf16x2(pack_bf16x2(x[2], x[3]), cm.y),
+                         w2 = mask_pos_bf16x2(pack_bf16x2(x[4], x[5]), cm.z), w3 = mask_pos_bf16x2(pack_bf16x2(x[6], x[7]), cm.w);
+          st_shared_v4(a_img + o, w0, w1, w2, w3);
+          *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_act + 8 * slot);
+      for (int bl = 1; bl <= 9; ++bl) {
+        mbar_wait(bar_acc + 8 * slot, acc_parity, 500 + bl);
+        acc_parity ^= 1;
+        tc_fence_after();
+        // ReLU mask source: bl=2 -> h7, ..., bl=9 -> h0; layers_2 (bl=1 output delta_g) has no activation
+        const uint8_t* himg = (bl >= 2) ? p.saved + saved_tensor_off(9 - bl, T) + (size_t)tile * 65536 : nullptr;
+        uint8_t* dsave = p.dscr + delta_tensor_off(bl, T) + (size_t)tile * 65536;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(t_lane + c * 32, acc);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(acc[i]);
+          if (bl == 2) {  // sigma head reads h7 too: + d_sigma * w_sigma   (utils/nets.py:40)
+            const float* ws = f32sec + kF32WSig + c * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + q);
+              x[4 * q] = fmaf(g.w, w4.x, x[4 * q]);
+              x[4 * q + 1] = fmaf(g.w, w4.y, x[4 * q + 1]);
+              x[4 * q + 2] = fmaf(g.w, w4.z, x[4 * q + 2]);
+              x[4 * q + 3] = fmaf(g.w, w4.w, x[4 * q + 3]);
+            }
+          }
+          const uint32_t kb = c >> 1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t o = kb * 16384u + sw128_off(r, (c & 1) * 4 + q);
+            uint32_t w0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), w1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                     w2 = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), w3 = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
+            if (himg) {
+              const uint4 hm = __ldg(reinterpret_cast<const uint4*>(himg + o));
+              w0 = mask_pos_bf16x2(w0, hm.x); w1 = mask_pos_bf16x2(w1, hm.y);
+              w2 = mask_pos_bf16x2(w2, hm.z); w3 = mask_pos_bf16x2(w3, hm.w);
+            }
+            if (bl < 9) st_shared_v4(a_img + o, w0, w1, w2, w3);
+            *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
+          }
+        }
+        if (bl < 9) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_act + 8 * slot);
+        } else {
+          tc_fence_before();
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
+        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
+        int s0 = 0;
+        for (int bl = 1; bl <= 9; ++bl) {
+          int s1 = s0;
+          while (!c_layout.bwd[s1].last) ++s1;
+          for (int slot = 0; slot < nslots; ++slot) {
+            for (int s = s0; s <= s1; ++s) {
+              mbar_wait(bar_wempty + 8 * stage, phase ^ 1, 600);
+              mbar_arrive_expect_tx(bar_wfull + 8 * stage, c_layout.bwd[s].bytes);
+              tma_bulk_g2s(smem_base + kBwdSmemW + stage * kWStageBytes, p.packed + c_layout.bwd[s].off,
+                           c_layout.bwd[s].bytes, bar_wfull + 8 * stage);
+              if (++stage == kBwdWStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          s0 = s1 + 1;
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t act_parity[2] = {0, 0};
+      const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
+        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
+        int s0 = 0;
+        for (int bl = 1; bl <= 9; ++bl) {
+          int s1 = s0;
+          while (!c_layout.bwd[s1].last) ++s1;
+          for (int slot = 0; slot < nslots; ++slot) {
+            mbar_wait(bar_act + 8 * slot, act_parity[slot], 700 + bl);
+            act_parity[slot] ^= 1;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+            for (int s = s0; s <= s1; ++s) {
+              const SlabDesc& d = c_layout.bwd[s];
+              mbar_wait(bar_wfull + 8 * stage, phase, 800);
+              tc_fence_after();
+              const uint32_t a_addr = smem_base + kSmemA + slot * kABytes + d.kb * 16384u;
+              const uint32_t b_addr = smem_base + kBwdSmemW + stage * kWStageBytes;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(d_tmem, umma_smem_desc(a_addr + kk * 32, 16, 1024),
+                          umma_smem_desc(b_addr + kk * 32, 16, 1024), idesc, (d.first && kk == 0) ? 0u : 1u);
+              umma_commit(bar_wempty + 8 * stage);
+              if (++stage == kBwdWStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_acc + 8 * slot);
+          }
+          s0 = s1 + 1;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------- wgrad
+struct WItem {
+  const uint8_t* a_ptr;   // delta tensor (tile images): A operand, M = output features
+  const uint8_t* b_ptr;   // layer input tensor (tile images): B operand, N = input features
+  float* dW;              // gradient of the weight, row pitch ldw, first column col0
+  float* db;              // bias gradient or null
+  uint32_t a_tile_bytes, b_tile_bytes;
+  int ldw, col0, ncols, nrows;
+  int a_chunks;           // 64-column chunks of delta: 2 (128 outputs) or 4 (256 outputs)
+  int b_chunks;           // 64-column chunks of the input staged: 1 or 4
+  int n_mma;              // UMMA N: 256 or 64
+  int cost;               // relative cost per tile (KB staged), for the work split
+};
+constexpr int kMaxWItems = 12;
+struct WgradParams {
+  WItem items[kMaxWItems];
+  int num_items;
+  int64_t T;
+};
+
+constexpr int kWgStages = 6;
+constexpr uint32_t kWgStageBytes = 32768;  // 32 sample rows: A chunks 4 x 4 KB | B chunks 4 x 4 KB
+constexpr uint32_t kWgSmemBar = kWgStages * kWgStageBytes;  // 196608
+constexpr uint32_t kWgSmemLaunch = kWgSmemBar + 256 + 1024;
+constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 bias sums + flush
+
+struct WSeg { int item; int64_t t0, t1; };
+
+// Position x in the global cost sequence -> (item, tile).
+__device__ __forceinline__ void wg_locate(const WgradParams& p, int64_t x, int& item, int64_t& tile) {
+  int64_t cum = 0;
+  for (int i = 0; i < p.num_items; ++i) {
+    const int64_t span = (int64_t)p.items[i].cost * p.T;
+    if (x < cum + span) { item = i; tile = (x - cum) / p.items[i].cost; return; }
+    cum += span;
+  }
+  item = p.num_items; tile = 0;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kWgSmemBar;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 48, bar_accfull = bar_base + 96,
+                 bar_accempty = bar_base + 104, tmem_slot = bar_base + 112;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1 + 4);  // MMA commit + one arrive per bias warp
+    }
+    mbar_init(bar_accfull, 1);
+    mbar_init(bar_accempty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // this CTA's share of the (item, tile) sequence
+  int64_t total = 0;
+  for (int i = 0; i < p.num_items; ++i) total += (int64_t)p.items[i].cost * p.T;
+  const int64_t x0 = total * blockIdx.x / gridDim.x, x1 = total * (blockIdx.x + 1) / gridDim.x;
+  int i0, i1;
+  int64_t t0, t1;
+  wg_locate(p, x0, i0, t0);
+  if (blockIdx.x + 1 == gridDim.x) { i1 = p.num_items; t1 = 0; } else wg_locate(p, x1, i1, t1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = i0; it <= i1 && it < p.num_items; ++it) {
+        const WItem& w = p.items[it];
+        const int64_t tb = (it == i0) ? t0 : 0, te = (it == i1) ? t1 : p.T;
+        for (int64_t tile = tb; tile < te; ++tile) {
+          for (int sub = 0; sub < 4; ++sub) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1, 900);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(w.a_chunks + w.b_chunks) * 4096u);
+            const uint32_t dst = smem_base + stage * kWgStageBytes;
+            for (int c = 0; c < w.a_chunks; ++c)
+              tma_bulk_g2s(dst + c * 4096, w.a_ptr + (size_t)tile * w.a_tile_bytes + c * 16384 + sub * 4096, 4096,
+                           bar_full + 8 * stage);
+            for (int c = 0; c < w.b_chunks; ++c)
+              tma_bulk_g2s(dst + 16384 + c * 4096, w.b_ptr + (size_t)tile * w.b_tile_bytes + c * 16384 + sub * 4096,
+                           4096, bar_full + 8 * stage);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, accempty_parity = 1;  // first wait passes on a fresh barrier
+      for (int it = i0; it <= i1 && it < p.num_items; ++it) {
+        const WItem& w = p.items[it];
+        const int64_t tb = (it == i0) ? t0 : 0, te = (it == i1) ? t1 : p.T;
+        if (te <= tb) continue;
+        mbar_wait(bar_accempty, accempty_parity, 1000);  // previous segment flushed out of TMEM
+        accempty_parity ^= 1;
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, w.n_mma, 1, 1);  // both operands MN-major
+        const int halves = w.a_chunks >> 1;
+        bool first = true;
+        for (int64_t tile = tb; tile < te; ++tile) {
+          for (int sub = 0; sub < 4; ++sub) {
+            mbar_wait(bar_full + 8 * stage, phase, 1100);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * kWgStageBytes;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {  // 16 sample rows per MMA
+              const uint64_t bdesc = umma_smem_desc(sa + 16384 + ks * 2048, 4096, 1024);
+              for (int h = 0; h < halves; ++h)
+                umma_bf16(tmem_base + h * 256, umma_smem_desc(sa + h * 8192 + ks * 2048, 4096, 1024), bdesc, idesc,
+                          (first && ks == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(bar_accfull);
+      }
+    }
+  } else {
+    // warps 2..5: bias column sums while tiles stream, then TMEM -> atomics flush per segment
+    const int q = warp & 3;          // TMEM lane group this warp may read
+    const int cw = warp - 2;         // delta chunk this warp sums for the bias gradient
+    uint32_t stage = 0, phase = 0, accfull_parity = 0;
+    for (int it = i0; it <= i1 && it < p.num_items; ++it) {
+      const WItem& w = p.items[it];
+      const int64_t tb = (it == i0) ? t0 : 0, te = (it == i1) ? t1 : p.T;
+      if (te <= tb) continue;
+      float b0 = 0.f, b1 = 0.f;
+      const bool do_bias = (w.db != nullptr) && (cw < w.a_chunks);
+      for (int64_t tile = tb; tile < te; ++tile) {
+        for (int sub = 0; sub < 4; ++sub) {
+          mbar_wait(bar_full + 8 * stage, phase, 1200);
+          if (do_bias) {
+            const uint32_t base = smem_base + stage * kWgStageBytes + cw * 4096 + (lane & 3) * 4;
+#pragma unroll 8
+            for (int row = 0; row < 32; ++row) {
+              uint32_t v;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(base + row * 128 + ((((uint32_t)lane >> 2) ^ (row & 7)) << 4)));
+              b0 += __uint_as_float(v << 16);
+              b1 += __uint_as_float(v & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (do_bias) {
+        const int n = cw * 64 + 2 * lane;
+        if (n < w.nrows) atomicAdd(w.db + n, b0);
+        if (n + 1 < w.nrows) atomicAdd(w.db + n + 1, b1);
+      }
+      mbar_wait(bar_accfull, accfull_parity, 1300);
+      accfull_parity ^= 1;
+      tc_fence_after();
+      const int halves = w.a_chunks >> 1;
+      for (int h = 0; h < halves; ++h) {
+        const int n = h * 128 + q * 32 + lane;  // output feature (row of dW)
+        for (int c = 0; c * 32 < w.n_mma; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + (((uint32_t)q * 32u) << 16) + h * 256 + c * 32, acc);
+          tmem_ld_wait();
+          if (n < w.nrows) {
+            float* dst = w.dW + (size_t)n * w.ldw + w.col0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < w.ncols) atomicAdd(dst + i, __uint_as_float(acc[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------- head gradients
+// dW_sigma[256] = sum_m d_sigma[m] h7[m,:],  dW_c1[3,128] = sum_m d_rgb[m,:]^T c1[m,:], and both
+// biases.  Thread t < 128 owns h7 column pair t; thread 128+u (u < 64) owns c1 column pair u.
+__global__ void __launch_bounds__(256) mlp_head_grads_kernel(const uint8_t* __restrict__ saved, const float* __restrict__ d_out,
+                                                             int64_t M, int64_t T, int64_t tiles_per_block,
+                                                             float* __restrict__ gWsig, float* __restrict__ gbsig,
+                                                             float* __restrict__ gWc1, float* __restrict__ gbc1) {
+  const int t = threadIdx.x;
+  const int64_t tb = (int64_t)blockIdx.x * tiles_per_block;
+  const int64_t te = tb + tiles_per_block < T ? tb + tiles_per_block : T;
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool is_h = t < 128, is_c = (t >= 128 && t < 192);
+  const int cp = is_h ? t : t - 128;  // column pair
+  const uint32_t in_row = ((uint32_t)(cp & 31) >> 2), sub4 = (cp & 3) * 4, kb = cp >> 5;
+  for (int64_t tile = tb; tile < te; ++tile) {
+    const uint8_t* img = is_h ? saved + saved_tensor_off(7, T) + (size_t)tile * 65536
+                              : saved + saved_tensor_off(9, T) + (size_t)tile * 32768;
+    const int64_t m0 = tile * kTileM;
+#pragma unroll 4
+    for (int row = 0; row < kTileM; ++row) {
+      if (m0 + row >= M) break;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(d_out) + m0 + row);
+      if (is_h || is_c) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(img + kb * 16384u + row * 128u + ((in_row ^ (row & 7)) << 4) + sub4));
+        const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xFFFF0000u);
+        if (is_h) {
+          a[0] = fmaf(g.w, lo, a[0]); a[1] = fmaf(g.w, hi, a[1]);
+        } else {
+          a[0] = fmaf(g.x, lo, a[0]); a[1] = fmaf(g.x, hi, a[1]);
+          a[2] = fmaf(g.y, lo, a[2]); a[3] = fmaf(g.y, hi, a[3]);
+          a[4] = fmaf(g.z, lo, a[4]); a[5] = fmaf(g.z, hi, a[5]);
+        }
+      } else if (t == 192) {
+        bsum[0] += g.x; bsum[1] += g.y; bsum[2] += g.z; bsum[3] += g.w;
+      }
+    }
+  }
+  if (is_h) {
+    atomicAdd(gWsig + 2 * cp, a[0]);
+    atomicAdd(gWsig + 2 * cp + 1, a[1]);
+  } else if (is_c) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      atomicAdd(gWc1 + ch * 128 + 2 * cp, a[2 * ch]);
+      atomicAdd(gWc1 + ch * 128 + 2 * cp + 1, a[2 * ch + 1]);
+    }
+  } else if (t == 192) {
+    atomicAdd(gbc1, bsum[0]); atomicAdd(gbc1 + 1, bsum[1]); atomicAdd(gbc1 + 2, bsum[2]);
+    atomicAdd(gbsig, bsum[3]);
+  }
+}
