@@ -1,0 +1,449 @@
+// Fused layer-chain kernel, generation 2 (included inside namespace nb200 by mlp_tc.cu).
+//
+// Two CTAs of a cluster (one SM pair) run every MMA together: tcgen05.mma.cta_group::2 with
+// M = 256 (each CTA owns 128 sample rows and their accumulators in its own TMEM) and the N rows
+// of each weight slab split across the pair, so a CTA streams only HALF of every weight slab from
+// L2.  The slabs of a layer (<= 4 x 16 KB per CTA) stay resident in a 4-stage ring while BOTH
+// in-flight tiles (slots) of the CTA consume them, which cuts the L2->SM weight traffic of the
+// first-generation kernel (9.3 KB/sample, L2-bandwidth bound) by ~3.4x.
+//
+//   warps 0-7 / 8-15 : prologue + epilogue of slot 0 / 1.  Two warps share each TMEM lane group:
+//                      thread (warp%4)*32+lane <-> sample row <-> TMEM lane, warps 4-7 of a slot take
+//                      the upper half of the accumulator columns (the epilogue is the critical path:
+//                      it must finish inside the 2048 cycles the other slot's MMAs take)
+//   warp  16         : weight producer (TMA bulk copy of this CTA's half slab)
+//   warp  17         : leader CTA: MMA issuer.  peer CTA: forwards "my half slab landed" to the leader.
+//
+// The same skeleton runs the forward chain (FwdEpi) and the backward delta chain (DgradEpi); they
+// differ only in the slab schedule and in what the epilogue warps do with each accumulator.
+constexpr uint32_t kC_A = 0, kC_E = 2 * kABytes, kC_W = kC_E + 2 * kEBytes;
+constexpr int kCStages = 4;
+constexpr uint32_t kCStageBytes = 16384;
+constexpr uint32_t kC_Bar = kC_W + kCStages * kCStageBytes;  // 229376
+constexpr uint32_t kCSmemLaunch = kC_Bar + 256 + 1024;
+constexpr int kCThreads = 576;
+constexpr int kCProducerWarp = 16, kCMmaWarp = 17;
+// barrier offsets inside the barrier block
+constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128;
+
+__constant__ float c_f32[kF32Floats];  // biases / head weights of the net being run (uploaded per call)
+
+struct TileCtx {
+  int64_t tile;      // 128-row tile index
+  int slot;          // which in-flight tile of the CTA
+  int half;          // 0: accumulator columns [0,128), 1: [128,256)
+  uint32_t r;        // row in tile == TMEM lane
+  uint32_t rowoff;   // r * 128
+  uint32_t r7s;      // (r & 7) << 4
+  uint32_t a_img, e_img, t_lane;
+};
+__device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32_t j) {
+  return kb * 16384u + c.rowoff + ((j << 4) ^ c.r7s);
+}
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCThreads, 1)
+chain_kernel(const __grid_constant__ typename Epi::Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar = smem_base + kC_Bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCStages; ++i) {
+      mbar_init(bar + kB_WFull + 8 * i, 1);
+      mbar_init(bar + kB_WPeer + 8 * i, 1);
+      mbar_init(bar + kB_WEmpty + 8 * i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar + kB_Act + 8 * s, 16);  // one elected arrive per epilogue warp: 8 warps x 2 CTAs (leader's copy is used)
+      mbar_init(bar + kB_Acc + 8 * s, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kCMmaWarp) tmem_alloc_2cta(bar + kB_Tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bar + kB_Tmem));
+
+  // pair-tiles (256 rows) of this cluster: pt = cluster + k * num_clusters; slot = k & 1
+  const int64_t PT = (p.num_tiles + 1) / 2;
+  const int64_t C = num_clusters_x(), cid = cluster_id_x();
+  const int64_t my_pt = (cid < PT) ? (PT - cid + C - 1) / C : 0;
+  const SlabDesc* slabs = Epi::slabs();
+
+  if (warp < 16) {
+    // ============================ prologue + epilogue of one slot ============================
+    const int slot = warp >> 3;
+    TileCtx c;
+    c.slot = slot;
+    c.half = (warp >> 2) & 1;
+    c.r = (uint32_t)(warp & 3) * 32u + (uint32_t)lane;
+    c.rowoff = c.r * 128u;
+    c.r7s = (c.r & 7u) << 4;
+    c.a_img = smem_base + kC_A + slot * kABytes;
+    c.e_img = smem_base + kC_E + slot * kEBytes;
+    c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
+    const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
+    uint32_t acc_parity = 0;
+    typename Epi::State st;
+    for (int64_t k = slot; k < my_pt; k += 2) {
+      c.tile = 2 * (cid + k * C) + rank;
+      Epi::begin_tile(p, st, c);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(act_remote);
+      for (int l = 0; l < Epi::kNumLayers; ++l) {
+        mbar_wait(bar + kB_Acc + 8 * slot, acc_parity, 100 + l);
+        acc_parity ^= 1;
+        tc_fence_after();
+        Epi::layer(p, st, c, l);
+        tc_fence_before();
+        if (l + 1 < Epi::kNumLayers) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(act_remote);
+        }
+      }
+    }
+  } else if (warp == kCProducerWarp) {
+    // ==================================== weight producer ====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
+        const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
+        int s0 = 0;
+        for (int l = 0; l < Epi::kNumLayers; ++l) {
+          int s1 = s0;
+          while (!slabs[s1].last) ++s1;
+          const int reps = (nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;  // shared by both slots?
+          for (int rep = 0; rep < reps; ++rep) {
+            for (int s = s0; s <= s1; ++s) {
+              const uint32_t half = slabs[s].bytes >> 1;
+              mbar_wait(bar + kB_WEmpty + 8 * stage, phase ^ 1, 200);
+              mbar_arrive_expect_tx(bar + kB_WFull + 8 * stage, half);
+              tma_bulk_g2s(smem_base + kC_W + stage * kCStageBytes, p.packed + slabs[s].off + rank * half, half,
+                           bar + kB_WFull + 8 * stage);
+              if (++stage == kCStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          s0 = s1 + 1;
+        }
+      }
+    }
+  } else if (rank != 0) {
+    // ================== peer CTA: tell the leader when my half of a slab landed ==================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
+        const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
+        int s0 = 0;
+        for (int l = 0; l < Epi::kNumLayers; ++l) {
+          int s1 = s0;
+          while (!slabs[s1].last) ++s1;
+          const int reps = (nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;
+          for (int i = 0; i < reps * (s1 - s0 + 1); ++i) {
+            mbar_wait(bar + kB_WFull + 8 * stage, phase, 250);
+            mbar_arrive_cluster(mapa_shared(bar + kB_WPeer + 8 * stage, 0));
+            if (++stage == kCStages) { stage = 0; phase ^= 1; }
+          }
+          s0 = s1 + 1;
+        }
+      }
+    }
+  } else {
+    // ================================ leader CTA: MMA issuer ================================
+    // The whole warp walks the schedule convergently (loop state and descriptors stay in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    uint32_t stage = 0, phase = 0;
+    uint32_t act_parity0 = 0, act_parity1 = 0;
+    const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);  // LBO/SBO/version/swizzle bits
+    for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
+      const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
+      int s0 = 0;
+      for (int l = 0; l < Epi::kNumLayers; ++l) {
+        int s1 = s0;
+        while (!slabs[s1].last) ++s1;
+        const bool shared = (nslots == 2 && s1 - s0 + 1 <= kCStages);
+        const uint32_t stage0 = stage, phase0 = phase;
+        for (int slot = 0; slot < nslots; ++slot) {
+          if (slot == 0) { mbar_wait(bar + kB_Act, act_parity0, 300 + l); act_parity0 ^= 1; }
+          else { mbar_wait(bar + kB_Act + 8, act_parity1, 350 + l); act_parity1 ^= 1; }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+          const bool replay = shared && slot == 1;  // slabs already resident from slot 0's pass
+          if (replay) { stage = stage0; phase = phase0; }
+          for (int s = s0; s <= s1; ++s) {
+            if (!replay) {
+              mbar_wait(bar + kB_WFull + 8 * stage, phase, 400);
+              mbar_wait(bar + kB_WPeer + 8 * stage, phase, 450);
+              tc_fence_after();
+            }
+            const uint32_t a_addr = slabs[s].src ? (smem_base + kC_E + slot * kEBytes)
+                                                 : (smem_base + kC_A + slot * kABytes + slabs[s].kb * 16384u);
+            const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_base + kC_W + stage * kCStageBytes) >> 4) & 0x3FFFu);
+            const uint32_t idesc = umma_idesc_bf16(256, slabs[s].n, 0, 0);
+            const uint32_t first = slabs[s].first ? 0u : 1u;
+            const int ksteps = slabs[s].ksteps;
+            const bool release = !(shared && slot == 0);  // the last user frees the stage
+            if (elect_one()) {
+              umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, first);   // +2 in the address field = +32 bytes
+              umma_bf16_2cta(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              if (ksteps > 2) {
+                umma_bf16_2cta(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_bf16_2cta(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              }
+              if (release) umma_commit_2cta(bar + kB_WEmpty + 8 * stage);
+              if (s == s1) umma_commit_2cta(bar + kB_Acc + 8 * slot);
+            }
+            __syncwarp();
+            if (++stage == kCStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        s0 = s1 + 1;
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kCMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ============================================================================ forward
+struct FwdEpiParams {
+  int in_mode;
+  const float* in0;
+  const float* in1;
+  int64_t M;
+  int N;
+  const uint8_t* packed;
+  float* out;
+  uint8_t* saved;  // null for inference
+  int64_t num_tiles;
+};
+
+__device__ __forceinline__ void load_query_chain(const FwdEpiParams& p, int64_t m, float v[6]) {
+  if (p.in_mode == NB200_IN_POINTS) {
+    const float2* q = reinterpret_cast<const float2*>(p.in0 + m * 6);
+    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+  } else {
+    const int64_t ray = m / p.N;
+    const float2* q = reinterpret_cast<const float2*>(p.in0 + ray * 6);
+    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const float t = __ldg(p.in1 + m);
+    const float dx = b.y, dy = c.x, dz = c.y;
+    v[0] = __fadd_rn(a.x, __fmul_rn(dx, t));  // utils/rendering.py:34-36 (d un-normalised)
+    v[1] = __fadd_rn(a.y, __fmul_rn(dy, t));
+    v[2] = __fadd_rn(b.x, __fmul_rn(dz, t));
+    const float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));  // :37
+    v[3] = dx * inv; v[4] = dy * inv; v[5] = dz * inv;
+  }
+}
+
+// One hidden layer: accumulator (TMEM) + bias -> [ReLU] -> bf16 A operand of the next layer.  Each
+// thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
+// (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
+template <bool kRelu, bool kSigma, bool kSave>
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gsave, float& sigma) {
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {  // 4 steps of 32 columns
+    const int col0 = c.half * 128 + q * 32;
+    uint32_t a[32];
+    tmem_ld32(c.t_lane + col0, a);
+    tmem_ld_wait();
+    const float* b = c_f32 + bias_off + col0;
+    const float* ws = c_f32 + kF32WSig + col0;
+    const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]) + b[8 * j + e];
+      if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[8 * j + e], sigma);
+      }
+      uint32_t w0, w1, w2, w3;
+      if (kRelu) {
+        w0 = pack_bf16x2_relu(x[0], x[1]); w1 = pack_bf16x2_relu(x[2], x[3]);
+        w2 = pack_bf16x2_relu(x[4], x[5]); w3 = pack_bf16x2_relu(x[6], x[7]);
+      } else {
+        w0 = pack_bf16x2(x[0], x[1]); w1 = pack_bf16x2(x[2], x[3]);
+        w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
+      }
+      const uint32_t o = sw_off(c, kb, j0 + j);
+      st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+      if (kSave) *reinterpret_cast<uint4*>(gsave + o) = make_uint4(w0, w1, w2, w3);
+    }
+  }
+}
+
+__device__ __forceinline__ void slot_barrier(int slot) {  // the 256 epilogue threads of one slot
+  asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory");
+}
+
+template <bool kSave>
+struct FwdEpi {
+  using Params = FwdEpiParams;
+  static constexpr int kNumLayers = kNumMmaLayers;
+  struct State {
+    float v[6];
+    float sigma;
+    int64_t m_raw;
+    bool row_valid;
+  };
+  __device__ static const SlabDesc* slabs() { return c_layout.fwd; }
+
+  __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
+    st.m_raw = c.tile * kTileM + c.r;
+    st.row_valid = st.m_raw < p.M;
+    load_query_chain(p, st.row_valid ? st.m_raw : p.M - 1, st.v);
+    st.sigma = 0.f;
+    uint8_t* gs = kSave ? p.saved + saved_tensor_off(10, p.num_tiles) + (size_t)c.tile * 16384 : nullptr;
+    // posx -> E[slot] (K = 64); each half of the slot's threads stores 4 of the 8 16-byte chunks
+    if (c.half == 0) encode_row<kLp, 0, 4>(st.v, c.e_img, c.r, gs);
+    else encode_row<kLp, 4, 8>(st.v, c.e_img, c.r, gs);
+  }
+
+  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int ml) {
+    const int64_t T = p.num_tiles;
+    if (ml == 5) {
+      // posx has been consumed by the skip layer: the encoding buffer now carries posd (27 -> 64)
+      uint8_t* gs = kSave ? p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384 : nullptr;
+      if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, gs);
+      else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, gs);
+    }
+    if (ml < 9) {
+      uint8_t* gsave = kSave ? p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536 : nullptr;
+      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
+      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);  // layers_2: no act.
+      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
+    } else {
+      // color_fc.0 epilogue (128 columns, ReLU; this thread's half = 64 of them) + color_fc.2
+      // (128 -> 3) on CUDA cores; the two halves of a row meet through the (now free) E buffer
+      uint8_t* gsave = kSave ? p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768 : nullptr;
+      float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const int col0 = c.half * 64 + q * 32;
+        uint32_t a[32];
+        tmem_ld32(c.t_lane + col0, a);
+        tmem_ld_wait();
+        const float* b = c_f32 + kF32Bias + 9 * 256 + col0;
+        const float* w = c_f32 + kF32WC1 + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = fmaxf(__uint_as_float(a[8 * j + e]) + b[8 * j + e], 0.f);
+            rgb[0] = fmaf(x[e], w[8 * j + e], rgb[0]);
+            rgb[1] = fmaf(x[e], w[128 + 8 * j + e], rgb[1]);
+            rgb[2] = fmaf(x[e], w[256 + 8 * j + e], rgb[2]);
+          }
+          if (kSave)
+            *reinterpret_cast<uint4*>(gsave + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j))) =
+                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+        }
+      }
+      const uint32_t xaddr = c.e_img + c.r * 16u;
+      if (c.half == 1) st_shared_v4(xaddr, __float_as_uint(rgb[0]), __float_as_uint(rgb[1]), __float_as_uint(rgb[2]), __float_as_uint(st.sigma));
+      slot_barrier(c.slot);
+      if (c.half == 0) {
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xaddr));
+        if (st.row_valid)
+          reinterpret_cast<float4*>(p.out)[st.m_raw] =
+              make_float4(rgb[0] + o.x + c_f32[kF32BC1], rgb[1] + o.y + c_f32[kF32BC1 + 1], rgb[2] + o.z + c_f32[kF32BC1 + 2],
+                          st.sigma + o.w + c_f32[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
+      }
+      slot_barrier(c.slot);  // E[slot] may be re-encoded for the next tile only after the exchange was read
+    }
+  }
+};
+
+// ======================================================================= backward (dgrad)
+struct DgradEpi {
+  using Params = BwdParams;
+  static constexpr int kNumLayers = 9;  // bl = 1..9
+  struct State { float4 g; };
+  __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
+
+  __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
+    const int64_t T = p.num_tiles;
+    const int64_t m_raw = c.tile * kTileM + c.r;
+    st.g = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M carry zero gradient
+    if (m_raw < p.M) st.g = __ldg(reinterpret_cast<const float4*>(p.d_out) + m_raw);
+    // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
+    const uint8_t* c1img = p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768;
+    uint8_t* dsave = p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768;
+    const float* w = c_f32 + kF32WC1;
+    const uint32_t kb = (uint32_t)c.half;  // 128 columns: each half of the slot's threads takes 64
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = sw_off(c, kb, j);
+      const uint4 cm = __ldg(reinterpret_cast<const uint4*>(c1img + o));
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = c.half * 64 + j * 8 + e;
+        x[e] = fmaf(st.g.z, w[256 + col], fmaf(st.g.y, w[128 + col], st.g.x * w[col]));
+      }
+      const uint32_t w0 = mask_pos_bf16x2(pack_bf16x2(x[0], x[1]), cm.x), w1 = mask_pos_bf16x2(pack_bf16x2(x[2], x[3]), cm.y),
+                     w2 = mask_pos_bf16x2(pack_bf16x2(x[4], x[5]), cm.z), w3 = mask_pos_bf16x2(pack_bf16x2(x[6], x[7]), cm.w);
+      st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+      *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
+    }
+  }
+
+  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
+    const int bl = l + 1;
+    const int64_t T = p.num_tiles;
+    // ReLU mask source: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (layers_2 has no activation)
+    const uint8_t* himg = (bl >= 2) ? p.saved + saved_tensor_off(9 - bl, T) + (size_t)c.tile * 65536 : nullptr;
+    uint8_t* dsave = p.dscr + delta_tensor_off(bl, T) + (size_t)c.tile * 65536;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int col0 = c.half * 128 + q * 32;
+      const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
+      uint4 hm[4];
+      if (himg) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hm[j] = __ldg(reinterpret_cast<const uint4*>(himg + sw_off(c, kb, j0 + j)));
+      }
+      uint32_t a[32];
+      tmem_ld32(c.t_lane + col0, a);
+      tmem_ld_wait();
+      const float* ws = c_f32 + kF32WSig + col0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          x[e] = __uint_as_float(a[8 * j + e]);
+          if (bl == 2) x[e] = fmaf(st.g.w, ws[8 * j + e], x[e]);  // + d_sigma * w_sigma (sigma head reads h7)
+        }
+        uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
+                 w3 = pack_bf16x2(x[6], x[7]);
+        if (himg) {
+          w0 = mask_pos_bf16x2(w0, hm[j].x); w1 = mask_pos_bf16x2(w1, hm[j].y);
+          w2 = mask_pos_bf16x2(w2, hm[j].z); w3 = mask_pos_bf16x2(w3, hm[j].w);
+        }
+        const uint32_t o = sw_off(c, kb, j0 + j);
+        if (bl < 9) st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+        *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
+      }
+    }
+  }
+};

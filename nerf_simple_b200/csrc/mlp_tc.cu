@@ -15,6 +15,9 @@
 // Shared memory (bytes, 1024-aligned):  A[2] 2x64 KB (128 x 256 bf16, 4 K-blocks of 128 B rows,
 // SWIZZLE_128B) | E[2] 2x16 KB (encoded input: posx 63->64, later posd 27->32) | W ring 2x32 KB.
 // TMEM: 512 columns = two 128x256 fp32 accumulators.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -231,11 +234,12 @@ __device__ __forceinline__ void load_query_tc(const FwdParams& p, int64_t m, flo
 // cols [x0,x1,x2, per coordinate: sin(2^i x), cos(2^i x) ...], zero padded to NCH*8 columns.
 // Level 0 uses the accurate sincosf; higher levels the double-angle recurrence (abs. error
 // <= 2^i * 1e-7, far below bf16 resolution).
-template <int L, int NCH>
+template <int L, int J0, int J1>
 __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, uint32_t r, uint8_t* gsave) {
-  float f[NCH * 8];
+  // 64 columns = 8 chunks of 16 bytes; this call stores chunks [J0, J1) (columns beyond 3+6L are zero)
+  float f[64];
 #pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) f[i] = 0.f;
+  for (int i = 0; i < 64; ++i) f[i] = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     f[c] = x[c];
@@ -251,7 +255,7 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
     }
   }
 #pragma unroll
-  for (int j = 0; j < NCH; ++j) {
+  for (int j = J0; j < J1; ++j) {
     const uint32_t w0 = pack_bf16x2(f[8 * j], f[8 * j + 1]), w1 = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                    w2 = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), w3 = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
     st_shared_v4(img_base + sw128_off(r, j), w0, w1, w2, w3);
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
       const int64_t m = row_valid ? m_raw : p.M - 1;
       float v[6];
       load_query_tc(p, m, v);
-      encode_row<kLp, 8>(v, e_img, r,   // posx -> E[slot], K = 64
+      encode_row<kLp, 0, 8>(v, e_img, r,   // posx -> E[slot], K = 64
                          kSave ? p.saved + saved_tensor_off(10, T) + (size_t)tile * 16384 : nullptr);
       fence_proxy_async_smem();
       tc_fence_before();
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
         const float* bias = f32sec + kF32Bias + ml * 256;
         if (ml == 5) {
           // posx has been consumed by the skip layer: the encoding buffer now carries posd
-          encode_row<kLd, 8>(v + 3, e_img, r,   // cols 27..63 zero: wgrad reads the image with N = 64
+          encode_row<kLd, 0, 8>(v + 3, e_img, r,   // cols 27..63 zero: wgrad reads the image with N = 64
                              kSave ? p.saved + saved_tensor_off(11, T) + (size_t)tile * 16384 : nullptr);
         }
         if (ml < 9) {
@@ -497,6 +501,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdPar
 }
 
 #include "mlp_tc_bwd.cuh"
+#include "mlp_chain.cuh"
 
 // ------------------------------------------------------------------------------ host API
 size_t tc_packed_bytes() {
@@ -525,6 +530,27 @@ static int check_arch() {
   return (arch / 10 == 10) ? NB200_OK : NB200_ERR_ARCH;
 }
 
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NB200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// biases / head weights of the net being run go to the constant bank (stream-ordered D2D copy)
+static int upload_consts(const void* packed, cudaStream_t s) {
+  NB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_f32, reinterpret_cast<const uint8_t*>(packed) + h_layout.f32_off,
+                                        kF32Floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+  return NB200_OK;
+}
+
+static int chain_grid(int64_t T) {
+  const int64_t PT = (T + 1) / 2;         // 256-row pair-tiles
+  const int64_t want = (PT + 1) / 2;      // two pair-tiles per cluster keep the ping-pong busy
+  const int64_t maxc = sm_count() / 2;
+  const int64_t clusters = want < maxc ? (want > 0 ? want : 1) : maxc;
+  return (int)(2 * clusters);
+}
+
 int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
                float* out, void* saved, void*, size_t, cudaStream_t s) {
   NB_TRY_RC(check_arch());
@@ -535,20 +561,40 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
                                        (int)kSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
     attr_set = true;
   }
-  FwdParams p;
+  const int64_t T = ceil_div64(M, kTileM);
+  if (use_v1()) {
+    FwdParams p;
+    p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
+    p.packed = reinterpret_cast<const uint8_t*>(packed);
+    p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
+    p.num_tiles = T;
+    const int64_t want = (p.num_tiles + 1) / 2;  // two tiles per CTA keep the ping-pong busy
+    const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
+    if (saved)
+      mlp_fwd_tc_kernel<true><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
+    else
+      mlp_fwd_tc_kernel<false><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
+    NB_LAUNCH_CHECK("mlp_fwd_tc_kernel");
+    return NB200_OK;
+  }
+  NB_TRY_RC(upload_consts(packed, s));
+  FwdEpiParams p;
   p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
-  p.num_tiles = ceil_div64(M, kTileM);
-  const int64_t want = (p.num_tiles + 1) / 2;  // two tiles per CTA keep the ping-pong busy
-  const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
+  p.num_tiles = T;
+  const int grid = chain_grid(T);
   if (saved)
-    mlp_fwd_tc_kernel<true><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
+    chain_kernel<FwdEpi<true>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
   else
-    mlp_fwd_tc_kernel<false><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
-  NB_LAUNCH_CHECK("mlp_fwd_tc_kernel");
+    chain_kernel<FwdEpi<false>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
+  NB_LAUNCH_CHECK("chain_kernel<FwdEpi>");
   return NB200_OK;
 }
 
@@ -561,6 +607,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   if (!attr_set) {
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
     attr_set = true;
   }
   const int64_t T = ceil_div64(M, kTileM);
@@ -570,11 +617,15 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   BwdParams bp;
   bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
   bp.d_out = d_out; bp.dscr = ds;
-  {
+  if (use_v1()) {
     const int64_t want = (T + 1) / 2;
     const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
     mlp_dgrad_tc_kernel<<<grid, kFwdThreads, kSmemLaunch, s>>>(bp);
     NB_LAUNCH_CHECK("mlp_dgrad_tc_kernel");
+  } else {
+    NB_TRY_RC(upload_consts(packed, s));
+    chain_kernel<DgradEpi><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
+    NB_LAUNCH_CHECK("chain_kernel<DgradEpi>");
   }
   // 2. weight gradients: (delta tensor, input tensor) pairs
   WgradParams wp;
