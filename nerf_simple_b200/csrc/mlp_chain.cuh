@@ -121,14 +121,17 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         for (int l = 0; l < Epi::kNumLayers; ++l) {
           int s1 = s0;
           while (!slabs[s1].last) ++s1;
-          const int reps = (nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;  // shared by both slots?
+          const int reps = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;  // shared by both slots?
           for (int rep = 0; rep < reps; ++rep) {
             for (int s = s0; s <= s1; ++s) {
               const uint32_t half = slabs[s].bytes >> 1;
               mbar_wait(bar + kB_WEmpty + 8 * stage, phase ^ 1, 200);
+              if (p.dbg & 2) { mbar_arrive(bar + kB_WFull + 8 * stage); }
+              else {
               mbar_arrive_expect_tx(bar + kB_WFull + 8 * stage, half);
               tma_bulk_g2s(smem_base + kC_W + stage * kCStageBytes, p.packed + slabs[s].off + rank * half, half,
                            bar + kB_WFull + 8 * stage);
+              }
               if (++stage == kCStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -140,16 +143,19 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // ================== peer CTA: tell the leader when my half of a slab landed ==================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      uint32_t peer_bar[kCStages];
+#pragma unroll
+      for (int i = 0; i < kCStages; ++i) peer_bar[i] = mapa_shared(bar + kB_WPeer + 8 * i, 0);
       for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
         const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
         int s0 = 0;
         for (int l = 0; l < Epi::kNumLayers; ++l) {
           int s1 = s0;
           while (!slabs[s1].last) ++s1;
-          const int reps = (nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;
+          const int reps = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;
           for (int i = 0; i < reps * (s1 - s0 + 1); ++i) {
             mbar_wait(bar + kB_WFull + 8 * stage, phase, 250);
-            mbar_arrive_cluster(mapa_shared(bar + kB_WPeer + 8 * stage, 0));
+            mbar_arrive_cluster(stage == 0 ? peer_bar[0] : (stage == 1 ? peer_bar[1] : (stage == 2 ? peer_bar[2] : peer_bar[3])));
             if (++stage == kCStages) { stage = 0; phase ^= 1; }
           }
           s0 = s1 + 1;
@@ -162,6 +168,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // registers); one elected lane issues the tcgen05 instructions.
     uint32_t stage = 0, phase = 0;
     uint32_t act_parity0 = 0, act_parity1 = 0;
+    long long t_act = 0, t_wfull = 0, t_wpeer = 0, t_begin = clock64();
     const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);  // LBO/SBO/version/swizzle bits
     for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
       const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
@@ -169,19 +176,24 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         int s1 = s0;
         while (!slabs[s1].last) ++s1;
-        const bool shared = (nslots == 2 && s1 - s0 + 1 <= kCStages);
+        const bool shared = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages);
         const uint32_t stage0 = stage, phase0 = phase;
         for (int slot = 0; slot < nslots; ++slot) {
+          long long tw0 = clock64();
           if (slot == 0) { mbar_wait(bar + kB_Act, act_parity0, 300 + l); act_parity0 ^= 1; }
           else { mbar_wait(bar + kB_Act + 8, act_parity1, 350 + l); act_parity1 ^= 1; }
+          t_act += clock64() - tw0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
           const bool replay = shared && slot == 1;  // slabs already resident from slot 0's pass
           if (replay) { stage = stage0; phase = phase0; }
           for (int s = s0; s <= s1; ++s) {
             if (!replay) {
+              long long tw1 = clock64();
               mbar_wait(bar + kB_WFull + 8 * stage, phase, 400);
+              long long tw2 = clock64();
               mbar_wait(bar + kB_WPeer + 8 * stage, phase, 450);
+              t_wfull += tw2 - tw1; t_wpeer += clock64() - tw2;
               tc_fence_after();
             }
             const uint32_t a_addr = slabs[s].src ? (smem_base + kC_E + slot * kEBytes)
@@ -209,6 +221,14 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         s0 = s1 + 1;
       }
     }
+    if constexpr (Epi::kHasDbg) {
+      if ((p.dbg & 8) && lane == 0 && p.dbg_counters) {
+        atomicAdd(p.dbg_counters + 0, (unsigned long long)t_act);
+        atomicAdd(p.dbg_counters + 1, (unsigned long long)t_wfull);
+        atomicAdd(p.dbg_counters + 2, (unsigned long long)t_wpeer);
+        atomicAdd(p.dbg_counters + 3, (unsigned long long)(clock64() - t_begin));
+      }
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -221,6 +241,8 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
 
 // ============================================================================ forward
 struct FwdEpiParams {
+  int dbg;
+  unsigned long long* dbg_counters;
   int in_mode;
   const float* in0;
   const float* in1;
@@ -255,37 +277,55 @@ __device__ __forceinline__ void load_query_chain(const FwdEpiParams& p, int64_t 
 // thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
 // (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gsave, float& sigma) {
-#pragma unroll 1
-  for (int q = 0; q < 4; ++q) {  // 4 steps of 32 columns
-    const int col0 = c.half * 128 + q * 32;
-    uint32_t a[32];
-    tmem_ld32(c.t_lane + col0, a);
-    tmem_ld_wait();
-    const float* b = c_f32 + bias_off + col0;
-    const float* ws = c_f32 + kF32WSig + col0;
-    const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
+__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, uint8_t* gsave,
+                                           float& sigma) {
+  const float* b = c_f32 + bias_off + col0;
+  const float* ws = c_f32 + kF32WSig + col0;
+  const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x[8];
+  for (int j = 0; j < 2; ++j) {
+    float x[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(b + 8 * j), b1 = *reinterpret_cast<const float4*>(b + 8 * j + 4);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]) + b[8 * j + e];
-      if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
+    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
+    add_f32x2(x[0], x[1], b0.x, b0.y); add_f32x2(x[2], x[3], b0.z, b0.w);
+    add_f32x2(x[4], x[5], b1.x, b1.y); add_f32x2(x[6], x[7], b1.z, b1.w);
+    if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[8 * j + e], sigma);
-      }
-      uint32_t w0, w1, w2, w3;
-      if (kRelu) {
-        w0 = pack_bf16x2_relu(x[0], x[1]); w1 = pack_bf16x2_relu(x[2], x[3]);
-        w2 = pack_bf16x2_relu(x[4], x[5]); w3 = pack_bf16x2_relu(x[6], x[7]);
-      } else {
-        w0 = pack_bf16x2(x[0], x[1]); w1 = pack_bf16x2(x[2], x[3]);
-        w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
-      }
-      const uint32_t o = sw_off(c, kb, j0 + j);
-      st_shared_v4(c.a_img + o, w0, w1, w2, w3);
-      if (kSave) *reinterpret_cast<uint4*>(gsave + o) = make_uint4(w0, w1, w2, w3);
+      for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[8 * j + e], sigma);
     }
+    uint32_t w0, w1, w2, w3;
+    if (kRelu) {
+      w0 = pack_bf16x2_relu(x[0], x[1]); w1 = pack_bf16x2_relu(x[2], x[3]);
+      w2 = pack_bf16x2_relu(x[4], x[5]); w3 = pack_bf16x2_relu(x[6], x[7]);
+    } else {
+      w0 = pack_bf16x2(x[0], x[1]); w1 = pack_bf16x2(x[2], x[3]);
+      w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
+    }
+    const uint32_t o = sw_off(c, kb, j0 + j);
+    st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+    if (kSave) *reinterpret_cast<uint4*>(gsave + o) = make_uint4(w0, w1, w2, w3);
+  }
+}
+
+// One hidden layer: accumulator (TMEM) + bias -> [ReLU] -> bf16 A operand of the next layer.  Each
+// thread converts the 128 columns of its half in 16-column steps, with the TMEM load of the next
+// step in flight while the current one is converted (double buffer); ReLU is fused into the
+// fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), biases come from the constant bank and are
+// added two at a time (add.f32x2).
+template <bool kRelu, bool kSigma, bool kSave>
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gsave, float& sigma) {
+  const int cbase = c.half * 128;
+  uint32_t a0[16], a1[16];
+  tmem_ld16(c.t_lane + cbase, a0);
+#pragma unroll 1
+  for (int q = 0; q < 8; q += 2) {
+    tmem_ld_wait();                                       // a0 (step q) has landed
+    tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);       // step q+1 in flight
+    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, gsave, sigma);
+    tmem_ld_wait();                                       // a1 has landed
+    if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
+    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, gsave, sigma);
   }
 }
 
@@ -296,6 +336,7 @@ __device__ __forceinline__ void slot_barrier(int slot) {  // the 256 epilogue th
 template <bool kSave>
 struct FwdEpi {
   using Params = FwdEpiParams;
+  static constexpr bool kHasDbg = true;
   static constexpr int kNumLayers = kNumMmaLayers;
   struct State {
     float v[6];
@@ -324,6 +365,7 @@ struct FwdEpi {
       if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, gs);
       else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, gs);
     }
+    if ((p.dbg & 1) && ml < 9) return;
     if (ml < 9) {
       uint8_t* gsave = kSave ? p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536 : nullptr;
       if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
@@ -376,6 +418,7 @@ struct FwdEpi {
 // ======================================================================= backward (dgrad)
 struct DgradEpi {
   using Params = BwdParams;
+  static constexpr bool kHasDbg = false;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   struct State { float4 g; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }

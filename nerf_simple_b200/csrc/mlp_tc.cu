@@ -585,6 +585,17 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   }
   NB_TRY_RC(upload_consts(packed, s));
   FwdEpiParams p;
+  { const char* e = getenv("NB200_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg_counters = nullptr;
+  if (p.dbg & 8) {
+    static unsigned long long* ctr = nullptr;
+    if (!ctr) { cudaMalloc(&ctr, 64); }
+    unsigned long long h[4];
+    cudaMemcpy(h, ctr, 32, cudaMemcpyDeviceToHost);   // counters of the previous launch (debug only; syncs)
+    printf("nb200 dbg: mma-warp cycles wait_act=%llu wait_wfull=%llu wait_wpeer=%llu total=%llu\n", h[0], h[1], h[2], h[3]);
+    cudaMemset(ctr, 0, 64);
+    p.dbg_counters = ctr;
+  }
   p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
@@ -615,6 +626,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   uint8_t* ds = reinterpret_cast<uint8_t*>(scratch);
   // 1. fused delta chain
   BwdParams bp;
+  bp.dbg = 0;
   bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
   bp.d_out = d_out; bp.dscr = ds;
   if (use_v1()) {
