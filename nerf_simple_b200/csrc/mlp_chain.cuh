@@ -126,12 +126,11 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
             for (int s = s0; s <= s1; ++s) {
               const uint32_t half = slabs[s].bytes >> 1;
               mbar_wait(bar + kB_WEmpty + 8 * stage, phase ^ 1, 200);
-              if (p.dbg & 2) { mbar_arrive(bar + kB_WFull + 8 * stage); }
-              else {
-              mbar_arrive_expect_tx(bar + kB_WFull + 8 * stage, half);
-              tma_bulk_g2s(smem_base + kC_W + stage * kCStageBytes, p.packed + slabs[s].off + rank * half, half,
-                           bar + kB_WFull + 8 * stage);
-              }
+              // both CTAs signal the LEADER's barrier: it expects the whole slab (two halves)
+              if (rank == 0) mbar_arrive_expect_tx(bar + kB_WFull + 8 * stage, slabs[s].bytes);
+              const int32_t row0 = (int32_t)(slabs[s].off >> 7) + (int32_t)(rank * (half >> 7));
+              tma_tensor2d_g2s_2cta(smem_base + kC_W + stage * kCStageBytes, half == 16384u ? &p.tmap128 : &p.tmap64, 0, row0,
+                                    mapa_shared(bar + kB_WFull + 8 * stage, 0));
               if (++stage == kCStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -140,28 +139,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       }
     }
   } else if (rank != 0) {
-    // ================== peer CTA: tell the leader when my half of a slab landed ==================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t peer_bar[kCStages];
-#pragma unroll
-      for (int i = 0; i < kCStages; ++i) peer_bar[i] = mapa_shared(bar + kB_WPeer + 8 * i, 0);
-      for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
-        const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
-        int s0 = 0;
-        for (int l = 0; l < Epi::kNumLayers; ++l) {
-          int s1 = s0;
-          while (!slabs[s1].last) ++s1;
-          const int reps = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;
-          for (int i = 0; i < reps * (s1 - s0 + 1); ++i) {
-            mbar_wait(bar + kB_WFull + 8 * stage, phase, 250);
-            mbar_arrive_cluster(stage == 0 ? peer_bar[0] : (stage == 1 ? peer_bar[1] : (stage == 2 ? peer_bar[2] : peer_bar[3])));
-            if (++stage == kCStages) { stage = 0; phase ^= 1; }
-          }
-          s0 = s1 + 1;
-        }
-      }
-    }
+    // peer CTA: nothing to issue (its MMAs are issued by the leader, its TMA signals the leader)
   } else {
     // ================================ leader CTA: MMA issuer ================================
     // The whole warp walks the schedule convergently (loop state and descriptors stay in uniform
@@ -191,9 +169,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
             if (!replay) {
               long long tw1 = clock64();
               mbar_wait(bar + kB_WFull + 8 * stage, phase, 400);
-              long long tw2 = clock64();
-              mbar_wait(bar + kB_WPeer + 8 * stage, phase, 450);
-              t_wfull += tw2 - tw1; t_wpeer += clock64() - tw2;
+              t_wfull += clock64() - tw1;
               tc_fence_after();
             }
             const uint32_t a_addr = slabs[s].src ? (smem_base + kC_E + slot * kEBytes)
@@ -241,6 +217,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
 
 // ============================================================================ forward
 struct FwdEpiParams {
+  CUtensorMap tmap128, tmap64;  // packed weight image as [rows x 128 B], boxes of 128 / 64 rows
   int dbg;
   unsigned long long* dbg_counters;
   int in_mode;

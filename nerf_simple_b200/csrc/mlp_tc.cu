@@ -15,6 +15,7 @@
 // Shared memory (bytes, 1024-aligned):  A[2] 2x64 KB (128 x 256 bf16, 4 K-blocks of 128 B rows,
 // SWIZZLE_128B) | E[2] 2x16 KB (encoded input: posx 63->64, later posd 27->32) | W ring 2x32 KB.
 // TMEM: 512 columns = two 128x256 fp32 accumulators.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -543,6 +544,48 @@ static int upload_consts(const void* packed, cudaStream_t s) {
   return NB200_OK;
 }
 
+// Tensor maps over the packed weight image (plain [rows x 64 bf16] view, no TMA swizzle: the image
+// is pre-swizzled), cached per packed buffer.  cuTensorMapEncodeTiled is fetched through the runtime
+// so the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapPair { const void* packed; CUtensorMap m128, m64; };
+static int get_tmaps(const void* packed, const TmapPair** out) {
+  static TmapPair cache[8];
+  static int used = 0, next = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].packed == packed) { *out = &cache[i]; return NB200_OK; }
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return NB200_ERR_CUDA;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  TmapPair& t = cache[next];
+  next = (next + 1) % 8;
+  if (used < 8) ++used;
+  t.packed = nullptr;
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)(h_layout.f32_off / 128)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t estride[2] = {1, 1};
+  for (int k = 0; k < 2; ++k) {
+    const cuuint32_t box[2] = {64, k == 0 ? 128u : 64u};
+    CUresult r = encode(k == 0 ? &t.m128 : &t.m64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), gdim, gstride,
+                        box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+      return NB200_ERR_CUDA;
+    }
+  }
+  t.packed = packed;
+  *out = &t;
+  return NB200_OK;
+}
+
 static int chain_grid(int64_t T) {
   const int64_t PT = (T + 1) / 2;         // 256-row pair-tiles
   const int64_t want = (PT + 1) / 2;      // two pair-tiles per cluster keep the ping-pong busy
@@ -584,7 +627,10 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
     return NB200_OK;
   }
   NB_TRY_RC(upload_consts(packed, s));
+  const TmapPair* tm = nullptr;
+  NB_TRY_RC(get_tmaps(packed, &tm));
   FwdEpiParams p;
+  p.tmap128 = tm->m128; p.tmap64 = tm->m64;
   { const char* e = getenv("NB200_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.dbg_counters = nullptr;
   if (p.dbg & 8) {
@@ -636,6 +682,9 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     NB_LAUNCH_CHECK("mlp_dgrad_tc_kernel");
   } else {
     NB_TRY_RC(upload_consts(packed, s));
+    const TmapPair* tm = nullptr;
+    NB_TRY_RC(get_tmaps(packed, &tm));
+    bp.tmap128 = tm->m128; bp.tmap64 = tm->m64;
     chain_kernel<DgradEpi><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
     NB_LAUNCH_CHECK("chain_kernel<DgradEpi>");
   }

@@ -18,6 +18,7 @@ __host__ __device__ __forceinline__ size_t delta_tensor_off(int t, int64_t num_t
 }
 
 struct BwdParams {
+  CUtensorMap tmap128, tmap64;
   int dbg;
   int64_t M;
   int64_t num_tiles;

@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_
       : "memory");
 }
 
+// 2-D tiled TMA load issued by either CTA of a pair; the transaction bytes are signalled on `bar`,
+// which may live in the PEER CTA (.cta_group::2) -- the leader's weight barrier counts both halves
+// of a slab without a forwarding hop.  `bar` is a shared::cluster address (mapa).
+__device__ __forceinline__ void tma_tensor2d_g2s_2cta(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1,
+                                                      uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
