@@ -121,7 +121,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         for (int l = 0; l < Epi::kNumLayers; ++l) {
           int s1 = s0;
           while (!slabs[s1].last) ++s1;
-          const int reps = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;  // shared by both slots?
+          const int reps = (nslots == 2 && s1 - s0 + 1 <= kCStages) ? 1 : nslots;  // shared by both slots?
           for (int rep = 0; rep < reps; ++rep) {
             for (int s = s0; s <= s1; ++s) {
               const uint32_t half = slabs[s].bytes >> 1;
@@ -154,7 +154,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         int s1 = s0;
         while (!slabs[s1].last) ++s1;
-        const bool shared = (!(p.dbg & 4) && nslots == 2 && s1 - s0 + 1 <= kCStages);
+        const bool shared = (nslots == 2 && s1 - s0 + 1 <= kCStages);
         const uint32_t stage0 = stage, phase0 = phase;
         for (int slot = 0; slot < nslots; ++slot) {
           long long tw0 = clock64();
@@ -342,7 +342,6 @@ struct FwdEpi {
       if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, gs);
       else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, gs);
     }
-    if ((p.dbg & 1) && ml < 9) return;
     if (ml < 9) {
       uint8_t* gsave = kSave ? p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536 : nullptr;
       if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
