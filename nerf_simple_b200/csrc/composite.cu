@@ -16,9 +16,17 @@ namespace nb200 {
 
 constexpr int kWarpsPerBlock = 8;
 
+// The kernels are HBM-bound only if the per-sample math stays around 100 instructions, so the
+// transcendental functions use the MUFU units (ex2/lg2.approx, <= 2^-21 relative error; the
+// compositing outputs stay within 5e-6 of the reference's libm-based fp32 math).
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
 __device__ __forceinline__ float softplus_ref(float x) {
   // F.softplus(beta=1, threshold=20): utils/rendering.py:67
-  return x > 20.f ? x : log1pf(expf(x));
+  // log1p(e) needs RELATIVE accuracy for tiny e: the last sample multiplies it by delta = 1e10 (:61),
+  // so below 1e-2 use the series e - e^2/2 + e^3/3 instead of log(1 + e).
+  const float e = __expf(x);
+  const float series = e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f);
+  return x > 20.f ? x : (e < 1e-2f ? series : __logf(1.f + e));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -35,9 +43,11 @@ __device__ __forceinline__ float dir_norm(const float* __restrict__ dirs, int64_
   if (dirs_mode == 0) {
     dx = __ldg(dirs + ray * 3); dy = __ldg(dirs + ray * 3 + 1); dz = __ldg(dirs + ray * 3 + 2);
   } else {
-    const float ax = __ldg(dirs + ray * 6 + 3), ay = __ldg(dirs + ray * 6 + 4), az = __ldg(dirs + ray * 6 + 5);
-    const float n = sqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax)));
-    dx = __fdiv_rn(ax, n); dy = __fdiv_rn(ay, n); dz = __fdiv_rn(az, n);
+    const float2* q = reinterpret_cast<const float2*>(dirs + ray * 6);
+    const float2 b = __ldg(q + 1), c = __ldg(q + 2);
+    const float ax = b.y, ay = c.x, az = c.y;
+    const float inv = rsqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax)));   // d/|d| to ~1 ulp (:37)
+    dx = ax * inv; dy = ay * inv; dz = az * inv;
   }
   return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 }
@@ -60,7 +70,7 @@ __device__ __forceinline__ void load_sample(const float* __restrict__ outs, cons
     s.t = __ldg(ts + g);
     const float d = (idx == N - 1) ? 1e10f : __fsub_rn(__ldg(ts + g + 1), s.t);  // :60-61
     s.delta = __fmul_rn(d, norm);                                               // :62
-    s.e = expf(__fmul_rn(-softplus_ref(s.o.w), s.delta));                        // :67
+    s.e = fast_exp(__fmul_rn(-softplus_ref(s.o.w), s.delta));                        // :67
     alpha = __fsub_rn(1.f, s.e);
     fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);                              // :68
   } else {
@@ -86,43 +96,103 @@ __device__ __forceinline__ float excl_cumprod(float fac, float& carry, int lane)
 }
 
 __device__ __forceinline__ float disparity(float depth, float acc) {
-  const float q = __fdiv_rn(depth, acc);                       // :82 depth / sum(weights)
+  const float q = __fdividef(depth, acc);                      // :82 depth / sum(weights)
   const float m = (q != q) ? q : fmaxf(1e-10f, q);             // torch.max propagates NaN
-  return __fdiv_rn(1.f, m);                                    // :83
+  return __frcp_rn(m);                                         // :83
 }
 
+// Sum 16 per-lane values across the warp with 16 shuffles (a butterfly that halves the number of
+// live values at every step); afterwards lane L holds the total of value L >> 1.
+__device__ __forceinline__ float warp_multi_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int d = 16, n = 8; d >= 2; d >>= 1, n >>= 1) {
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float keep = up ? v[i + n] : v[i];
+      const float send = up ? v[i] : v[i + n];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Forward: R rays per warp iteration with every load issued before any math (R*NCH independent
+// 512 B float4 requests + R*NCH 128 B ts requests in flight per warp), so the long dependent
+// softplus/exp/scan chains of one ray overlap the memory latency of the other.
+template <int NCH, int R, bool kFull>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(const float* __restrict__ outs, const float* __restrict__ ts,
                      const float* __restrict__ dirs, int dirs_mode, int64_t B, int N, float* __restrict__ rgb,
                      float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ alpha_out,
                      float* __restrict__ w_out) {
+  static_assert(R * 5 <= 16, "per-iteration sums must fit the 16-value warp reduction");
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  const int nch = (N + 31) >> 5;
-  for (int64_t ray = warp0; ray < B; ray += nwarps) {
-    const float norm = dir_norm(dirs, ray, dirs_mode);
-    float carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const int idx = c * 32 + lane;
-      SampleState s;
-      float a, fac;
-      load_sample(outs, ts, ray, N, idx, norm, s, a, fac);
-      const float T = excl_cumprod(fac, carry, lane);
-      const float w = a * T;
-      sr = fmaf(w, s.o.x, sr); sg = fmaf(w, s.o.y, sg); sb = fmaf(w, s.o.z, sb);
-      sd = fmaf(w, s.t, sd);
-      sa += w;
-      if (idx < N) {
-        if (alpha_out) alpha_out[ray * N + idx] = a;
-        if (w_out) w_out[ray * N + idx] = w;
+  for (int64_t ray0 = warp0 * R; ray0 < B; ray0 += nwarps * R) {
+    float4 o[R][NCH];
+    float t[R][NCH], tn[R][NCH];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t ray = ray0 + r < B ? ray0 + r : B - 1;   // tail: recompute the last ray, store predicated off
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int idx = c * 32 + lane;
+        const int64_t g = ray * N + ((kFull || idx < N) ? idx : N - 1);
+        o[r][c] = __ldg(reinterpret_cast<const float4*>(outs) + g);
+        t[r][c] = __ldg(ts + g);
       }
     }
-    sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
-    if (lane == 0) {
-      rgb[ray * 3] = sr; rgb[ray * 3 + 1] = sg; rgb[ray * 3 + 2] = sb;
-      disp[ray] = disparity(sd, sa);
-      acc[ray] = sa;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      // t[i+1]: neighbour lane, or lane 0 of the next chunk
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const float nxt = __shfl_down_sync(0xffffffffu, t[r][c], 1);
+        const float wrap = __shfl_sync(0xffffffffu, t[r][c + 1 < NCH ? c + 1 : c], 0);
+        tn[r][c] = (lane == 31) ? wrap : nxt;
+      }
+    }
+    float sums[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sums[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t ray = ray0 + r < B ? ray0 + r : B - 1;
+      const bool store = ray0 + r < B;
+      const float norm = dir_norm(dirs, ray, dirs_mode);
+      float carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int idx = c * 32 + lane;
+        const bool valid = kFull || idx < N;
+        const float d = (idx == N - 1) ? 1e10f : __fsub_rn(tn[r][c], t[r][c]);      // :60-61
+        const float delta = __fmul_rn(d, norm);                                     // :62
+        const float e = fast_exp(__fmul_rn(-softplus_ref(o[r][c].w), delta));       // :67
+        const float a = valid ? __fsub_rn(1.f, e) : 0.f;
+        const float fac = valid ? __fadd_rn(__fsub_rn(1.f, a), 1e-10f) : 1.f;       // :68
+        const float T = excl_cumprod(fac, carry, lane);
+        const float w = a * T;
+        sr = fmaf(w, o[r][c].x, sr); sg = fmaf(w, o[r][c].y, sg); sb = fmaf(w, o[r][c].z, sb);
+        sd = fmaf(w, t[r][c], sd);
+        sa += w;
+        if (valid && store) {
+          if (alpha_out) alpha_out[ray * N + idx] = a;
+          if (w_out) w_out[ray * N + idx] = w;
+        }
+      }
+      sums[r * 5] = sr; sums[r * 5 + 1] = sg; sums[r * 5 + 2] = sb; sums[r * 5 + 3] = sd; sums[r * 5 + 4] = sa;
+    }
+    // lane L now owns value L>>1 = 5*r + k: k = 0..2 rgb, 3 depth (needs acc: lane of value 5r+4), 4 acc
+    const float tot = warp_multi_sum16(sums, lane);
+    const int vi = lane >> 1, r = vi / 5, k = vi - 5 * r;
+    const float acc_r = __shfl_sync(0xffffffffu, tot, (5 * (r < R ? r : 0) + 4) * 2);
+    if (!(lane & 1) && r < R && ray0 + r < B) {
+      const int64_t ray = ray0 + r;
+      if (k < 3) rgb[ray * 3 + k] = tot;
+      else if (k == 3) disp[ray] = disparity(tot, acc_r);
+      else acc[ray] = tot;
     }
   }
 }
@@ -189,7 +259,7 @@ composite_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ t
         const float g_sp = (g_a * s.e) * s.delta;  // this order keeps 0*1e10 == 0
         float g_sigma = g_sp;
         if (!(s.o.w > 20.f)) {
-          const float z = expf(s.o.w);
+          const float z = fast_exp(s.o.w);
           g_sigma = g_sp * z / (z + 1.f);
         }
         reinterpret_cast<float4*>(d_outs)[ray * N + idx] = make_float4(w * gr, w * gg, w * gb, g_sigma);
@@ -268,7 +338,7 @@ __global__ void composite_bwd_serial_kernel(const float* __restrict__ outs, cons
     if (d_alpha) g_a += d_alpha[ray * N + i];
     const float g_sp = (g_a * s.e) * s.delta;
     float g_sigma = g_sp;
-    if (!(s.o.w > 20.f)) { const float z = expf(s.o.w); g_sigma = g_sp * z / (z + 1.f); }
+    if (!(s.o.w > 20.f)) { const float z = fast_exp(s.o.w); g_sigma = g_sp * z / (z + 1.f); }
     reinterpret_cast<float4*>(d_outs)[ray * N + i] = make_float4(w * gr, w * gg, w * gb, g_sigma);
     T *= fac;
   }
@@ -290,13 +360,27 @@ int nb200_composite_forward(const float* outs, const float* ts, const float* dir
   using namespace nb200;
   if (!outs || !ts || !dirs || !rgb || !disp || !acc || B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
   if (B == 0) return NB200_OK;
-  if (N <= 256) {
-    composite_fwd_kernel<<<warp_grid(B), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
-        outs, ts, dirs, dirs_mode, B, N, rgb, disp, acc, alpha, weights);
-  } else {
+  cudaStream_t s = as_stream(stream);
+#define NB_FWD(NCH, R)                                                                                       \
+  do {                                                                                                       \
+    if (N == NCH * 32)                                                                                       \
+      composite_fwd_kernel<NCH, R, true><<<warp_grid((B + R - 1) / R), kWarpsPerBlock * 32, 0, s>>>(         \
+          outs, ts, dirs, dirs_mode, B, N, rgb, disp, acc, alpha, weights);                                  \
+    else                                                                                                     \
+      composite_fwd_kernel<NCH, R, false><<<warp_grid((B + R - 1) / R), kWarpsPerBlock * 32, 0, s>>>(        \
+          outs, ts, dirs, dirs_mode, B, N, rgb, disp, acc, alpha, weights);                                  \
+  } while (0)
+  if (N <= 32) NB_FWD(1, 3);
+  else if (N <= 64) NB_FWD(2, 2);
+  else if (N <= 96) NB_FWD(3, 2);
+  else if (N <= 128) NB_FWD(4, 2);
+  else if (N <= 192) NB_FWD(6, 1);
+  else if (N <= 256) NB_FWD(8, 1);
+  else {
     composite_fwd_serial_kernel<<<(unsigned)ceil_div64(B, 128), 128, 0, as_stream(stream)>>>(
         outs, ts, dirs, dirs_mode, B, N, rgb, disp, acc, alpha, weights);
   }
+#undef NB_FWD
   NB_LAUNCH_CHECK("composite_fwd_kernel");
   return NB200_OK;
 }

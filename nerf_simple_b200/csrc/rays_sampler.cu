@@ -95,9 +95,13 @@ __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restr
       r[0] = u01(x.x); r[1] = u01(x.y); r[2] = u01(x.z); r[3] = u01(x.w);
     }
     float o[4];
+    // one modulo per 4 samples (32-bit when the index allows), then wrap by compare
+    int i0 = (base >> 32) == 0 ? (int)((uint32_t)base % (uint32_t)N) : (int)((uint64_t)base % (uint32_t)N);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = (int)((base + k) % N);
+      int i = i0 + k;
+      i = i >= N ? i - N : i;
+      i = i >= N ? i % N : i;                        // N < 4 only
       // utils/rendering.py:29: bin_diff*unif + t_bins[:-1]; two roundings, never an fma
       o[k] = __fadd_rn(__fmul_rn(bin, r[k]), tbin(i, N, tn, tf, step));
     }
