@@ -64,18 +64,27 @@ class FrameRenderer:
         return out_rgb_pinned, out_disp_pinned
 
 
+def gather_shards(local, n_items, rank, world, group=None):
+    """all_gather of per-rank row blocks whose sizes follow `shard_range` (they differ by at most one
+    row, so every rank pads to the largest block; collectives need equal sizes)."""
+    import torch.distributed as dist
+    spans = [shard_range(n_items, r, world) for r in range(world)]
+    width = max(e - b for b, e in spans)
+    padded = local
+    if local.shape[0] < width:
+        padded = torch.cat([local, local.new_zeros((width - local.shape[0],) + tuple(local.shape[1:]))])
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[:e - b] for p, (b, e) in zip(parts, spans)])
+
+
 def render_sharded(renderer: FrameRenderer, poses_dev, idx, rank, world, gather=True):
     """Ray-sharded render of frame `idx`: each rank renders a contiguous band of rays; one
     all_gather of (rgb, disp) = 16 B/ray assembles the frame on every rank."""
-    import torch.distributed as dist
     n = renderer.H * renderer.W
     b, e = shard_range(n, rank, world)
     rgb, disp = renderer.render_rays(poses_dev, idx * n + b, e - b)
     if not gather or world == 1:
         return rgb, disp
-    packed = torch.cat([rgb, disp[:, None]], dim=1)                  # [n_local, 4]
-    sizes = [shard_range(n, r, world) for r in range(world)]
-    parts = [torch.empty((e2 - b2, 4), dtype=packed.dtype, device=packed.device) for b2, e2 in sizes]
-    dist.all_gather(parts, packed)
-    full = torch.cat(parts)
+    full = gather_shards(torch.cat([rgb, disp[:, None]], dim=1), n, rank, world)     # [n, 4]
     return full[:, :3].reshape(renderer.H, renderer.W, 3), full[:, 3].reshape(renderer.H, renderer.W)

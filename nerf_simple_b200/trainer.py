@@ -1,0 +1,129 @@
+"""Device-resident training step (the loop body of train.py:45-57 without the host round trips).
+
+The reference selects rays with a CPU `randperm` over the whole ray table (328 ms/step,
+utils/dataload.py:151), copies rays/colours/jitter to the GPU and runs ~700 ATen kernels.  Here
+the ray table and the ground-truth colours live on the device, a step is
+    select -> Philox jitter -> fused MLP forward (saving bf16 tiles) -> compositing forward ->
+    MSE gradient -> compositing backward -> delta chain -> wgrad -> [all-reduce] -> Adam
+and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
+needs exactly one NCCL all-reduce of 595,844 floats per step.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, config, ops
+from .ops import NUM_PARAMS
+
+
+def flatten_parameters(net):
+    """Re-home the 24 parameters of `net` as views of one flat buffer (state_dict unchanged)."""
+    params = list(net.parameters())
+    dev = params[0].device
+    flat = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        off += n
+    assert off == NUM_PARAMS
+    return flat
+
+
+def attach_flat_grad(net, device=None):
+    params = list(net.parameters())
+    flat = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=device or params[0].device)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad = flat[off:off + n].view(p.shape)
+        off += n
+    return flat
+
+
+def allreduce_mean_(flat_grad, world_size, group=None):
+    """Sum the flat gradient over ranks and divide by the world size (equal local batches =>
+    the global-batch mean of train.py:52).  Works with NCCL (GPU) and gloo (CPU tests)."""
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.mul_(1.0 / world_size)
+    return flat_grad
+
+
+class Trainer:
+    def __init__(self, net, rays_table, gt_table, N=64, batch_size=4096, lr=5e-4, lr_decay=1.0,
+                 tn=2.0, tf=6.0, seed=1, precision="bf16", world_size=1):
+        self.net, self.N, self.B = net, int(N), int(batch_size)
+        self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
+        self.precision = {"fp32": _lib.FP32, "bf16": _lib.BF16}[precision]
+        self.world_size = world_size
+        self.device = next(net.parameters()).device
+        self.rays_table = _lib.require_cuda(rays_table, "rays_table").float().contiguous()
+        self.gt_table = _lib.require_cuda(gt_table, "gt_table").float().contiguous()
+        self.flat_param = flatten_parameters(net)
+        self.flat_grad = attach_flat_grad(net)
+        self.params = net.kernel_params()
+        self.grads = [p.grad for p in self.params]
+        # train.py:43 Adam(lr=5e-4) with a per-step exponential decay (train.py:39,56-57)
+        self.opt = torch.optim.Adam([torch.nn.Parameter(self.flat_param)], lr=lr, fused=True)
+        self.opt.param_groups[0]["params"][0].grad = self.flat_grad
+        self.lr_decay = lr_decay
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        lib = _lib.load()
+        M = self.B * self.N
+        self._out = torch.empty((M, 4), dtype=torch.float32, device=self.device)
+        self._dout = torch.empty((M, 4), dtype=torch.float32, device=self.device)
+        self._saved = torch.empty(lib.nb200_mlp_saved_bytes(self.precision, M), dtype=torch.uint8, device=self.device)
+        self._scratch = torch.empty(max(16, lib.nb200_mlp_scratch_bytes(self.precision, M, 1)), dtype=torch.uint8,
+                                    device=self.device)
+        self._rgb = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
+        self._disp = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        self._acc = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        self._offset = 0
+        self.launches = 0
+        self.last_loss = None
+
+    def step(self, sync_loss=False):
+        lib = _lib.load()
+        dev, B, N, M = self.device, self.B, self.N, self.B * self.N
+        st = _lib.stream_ptr(dev)
+        # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
+        ids = torch.randint(0, self.rays_table.shape[0], (B,), device=dev, generator=self.gen)
+        rays = self.rays_table.index_select(0, ids)
+        gt = self.gt_table.index_select(0, ids)
+        ts = ops.stratified_ts(B, N, self.tn, self.tf, device=dev, seed=self.seed, offset=self._offset)
+        self._offset += (M + 3) // 4
+        packed = self.net._packed.get(self.params, self.precision)
+        pa = _lib.ptr_array(self.params)
+        _lib.check(lib.nb200_mlp_forward(self.precision, _lib.IN_RAYS, _lib.ptr(rays), _lib.ptr(ts), M, N, pa,
+                                         _lib.ptr(packed), _lib.ptr(self._out), _lib.ptr(self._saved), None, 0, st),
+                   "nb200_mlp_forward")
+        _lib.check(lib.nb200_composite_forward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, B, N,
+                                               _lib.ptr(self._rgb), _lib.ptr(self._disp), _lib.ptr(self._acc),
+                                               None, None, st), "nb200_composite_forward")
+        diff = self._rgb - gt                                  # MSELoss over B*3 (train.py:42,52)
+        loss = (diff * diff).mean()
+        d_rgb = diff * (2.0 / (3 * B))
+        _lib.check(lib.nb200_composite_backward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, _lib.ptr(d_rgb),
+                                                None, None, None, None, B, N, _lib.ptr(self._dout), st),
+                   "nb200_composite_backward")
+        self.flat_grad.zero_()
+        _lib.check(lib.nb200_mlp_backward(self.precision, _lib.IN_RAYS, _lib.ptr(rays), _lib.ptr(ts), M, N, pa,
+                                          _lib.ptr(packed), _lib.ptr(self._dout), _lib.ptr(self._saved),
+                                          _lib.ptr_array(self.grads), _lib.ptr(self._scratch),
+                                          self._scratch.numel(), st), "nb200_mlp_backward")
+        allreduce_mean_(self.flat_grad, self.world_size)
+        self.opt.step()
+        self._bump_versions()
+        if self.lr_decay != 1.0:
+            self.opt.param_groups[0]["lr"] *= self.lr_decay
+        self.launches += 9 if self.precision == _lib.BF16 else 60
+        self.last_loss = loss
+        return float(loss) if sync_loss else loss
+
+    def _bump_versions(self):
+        # the optimizer updated the flat buffer, not the 24 views: invalidate the packed-weight cache
+        self.net._packed.key = None
