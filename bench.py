@@ -97,23 +97,28 @@ class ClockSampler:
 # ------------------------------------------------------------------------- reference / CPU arm
 def oracle_render_sample(n_rays, N, chunk, seed=0):
     """Times the CPU restatement of the reference path on a bounded sample: `n_rays` rays of the
-    800x800 dome view, N samples/ray, `chunk`-ray chunks (configs[0] shape), no_grad render."""
-    from oracle import nerf_oracle as O   # CPU baseline leg only
-    P = O.init_params(seed)
+    800x800 dome view, N samples/ray, `chunk`-ray chunks (configs[0] shape), no_grad render.  The
+    port is the torch-CPU op sequence of the reference (oracle/nerf_oracle_torch.py) with all
+    intra-op threads; ray setup comes from the numpy oracle."""
+    import torch
+    from oracle import nerf_oracle as O        # CPU baseline leg only
+    from oracle import nerf_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count())
+    P = {k: torch.from_numpy(v) for k, v in O.init_params(seed).items()}
     f = 800 / (2 * np.tan(FOV / 2))
     poses = np.stack(O.poses_to_render(4, -30, 30))
     dirs = O.rays_single_cam(800, 800, f)
-    rng = np.random.default_rng(1)
     start = 800 * 400 + 100
-    rays = O.world_rays(poses[1:2], dirs[:, start:start + n_rays])
+    rays = torch.from_numpy(O.world_rays(poses[1:2], dirs[:, start:start + n_rays]))
+    torch.manual_seed(1)
 
     def run():
         t0 = time.perf_counter()
-        for s in range(0, n_rays, chunk):
-            r = rays[s:s + chunk]
-            u = rng.random((r.shape[0], N), dtype=np.float32)
-            rgb, *_ = O.render_nerf(r, P, N, u)
-            np.clip(rgb, 0, 1, out=rgb)
+        with torch.no_grad():
+            for s in range(0, n_rays, chunk):
+                r = rays[s:s + chunk]
+                rgb, *_ = OT.render_nerf(r, P, N, torch.rand(r.shape[0], N))
+                rgb.clamp_(0, 1)
         return time.perf_counter() - t0
     return run
 
@@ -129,7 +134,7 @@ def reference_arm(args, rank):
     ms = 1e3 * float(np.mean(times))
     val = n_rays / (ms * 1e-3)
     cores = os.cpu_count()
-    sample = f"{n_rays} rays of the 800x800 dome view x {N} samples, {chunk}-ray chunks, numpy fp32 (BLAS threads: all {cores} cores)"
+    sample = f"{n_rays} rays of the 800x800 dome view x {N} samples, {chunk}-ray chunks, torch-CPU fp32 port of the reference ops, {cores} intra-op threads"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -251,7 +256,7 @@ def b200_arm(args, rank, local_rank, world):
             tt = min(run() for _ in range(3))
             line["cpu_baseline"] = {"value": n_s / tt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{n_s} rays of the same 800x800 view x {N} samples in {chunk}-ray chunks, "
-                                              f"numpy fp32 restatement of the reference (oracle/), best of 3"}
+                                              f"torch-CPU fp32 port of the reference ops (oracle/), all cores, best of 3"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

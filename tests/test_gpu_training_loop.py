@@ -1,0 +1,95 @@
+"""GPU test of the host drivers exactly as train.py / test.py use them (train.py:33-82,
+test.py:25-45), on a synthetic Blender-format dataset: RayGenerator -> select -> render_nerf ->
+MSELoss -> backward -> Adam -> render_image -> state_dict round trip."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from synth_dataset import write_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    return write_dataset(str(tmp_path_factory.mktemp("blender")), H=16, W=16)
+
+
+def test_ray_generator_matches_reference_layout(dataset):
+    from nerf_simple_b200.dataload import RayGenerator, load_data
+    samples, cam = load_data(dataset, half_res=False)
+    assert [len(samples[k]) for k in ("train", "val", "test")] == [3, 2, 2]
+    H, W, f = cam
+    assert (H, W) == (16, 16) and abs(f - 16 / (2 * np.tan(0.6911112070083618 / 2))) < 1e-9
+    assert samples["train"][0]["img"].shape == (16, 16, 3) and samples["train"][0]["img"].dtype == np.float64
+    assert "img_depth" in samples["test"][0] and samples["train"][1]["metadata"]["file_path"] == "./train/r_1"
+    rg = RayGenerator(dataset, half_res=True)                    # INTER_AREA half-res like the reference
+    assert (rg.H, rg.W) == (8, 8) and rg.samples["val"][0]["img"].shape == (8, 8, 3)
+    assert not rg.rays_dataset["train"].is_cuda and rg.rays_dataset["train"].shape == (3 * 64, 6)
+    poses = np.stack([s["transform"].numpy() for s in rg.samples["train"]])
+    ref = O.world_rays(poses, O.rays_single_cam(8, 8, rg.f))     # utils/dataload.py:114-129
+    assert np.abs(rg.rays_dataset["train"].numpy() - ref).max() <= 1e-6
+    rays, ids = rg.select("train", N=50)
+    assert rays.shape == (50, 6) and torch.equal(rays, rg.rays_dataset["train"][ids])
+    rays, ids = rg.select_imgs("train", N=40, im_idxs=[1])
+    assert rays.shape == (40, 6) and ids.min() >= 64 and ids.max() < 128
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_train_loop_like_train_py(dataset, precision, tmp_path):
+    from nerf_simple_b200 import config
+    from nerf_simple_b200.dataload import RayGenerator
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.rendering import render_image, render_nerf
+    config.set_precision(precision)
+    config.set_sampler("reference")
+    torch.manual_seed(0)
+    rg = RayGenerator(dataset, half_res=False, num_imgs=2)
+    train_imgs = torch.stack([torch.from_numpy(s["img"]) for s in rg.samples["train"]]).reshape(-1, 3)
+    net = Nerf().cuda()
+    criterion = torch.nn.MSELoss()
+    optimizer = torch.optim.Adam(net.parameters(), lr=5e-4)
+    losses = []
+    for i in range(60):
+        rays, ray_ids = rg.select(mode="train", N=256)
+        gt = train_imgs[ray_ids, :].float().cuda()
+        optimizer.zero_grad()
+        rgb, depth, alpha, acc, w = render_nerf(rays.cuda(), net, 32)
+        loss = criterion(rgb, gt)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.item())
+    assert np.mean(losses[-10:]) < 0.5 * np.mean(losses[:5]), losses[::10]
+    rgb_img, depth_img, gt_img = render_image(net, rg, batch_size=100, im_idx=1, im_set="train")
+    assert rgb_img.shape == (1, 16, 16, 3) and depth_img.shape == (1, 16, 16, 1) and gt_img.shape == (1, 16, 16, 3)
+    mse = torch.mean((rgb_img - torch.from_numpy(gt_img).float()) ** 2)
+    assert torch.isfinite(mse)
+    # checkpoint round trip exactly like train.py:87 / test.py:28
+    path = str(tmp_path / "ckpt.pth")
+    torch.save(net.state_dict(), path)
+    net2 = Nerf().cuda()
+    net2.load_state_dict(torch.load(path), strict=True)
+    torch.manual_seed(5)
+    a = render_nerf(rg.rays_dataset["val"][:64].cuda(), net, 32)[0]
+    torch.manual_seed(5)
+    b = render_nerf(rg.rays_dataset["val"][:64].cuda(), net2, 32)[0]
+    assert torch.equal(a, b)
+    config.set_precision("bf16")
+
+
+def test_device_trainer_converges():
+    from nerf_simple_b200 import ops
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.trainer import Trainer
+    from nerf_simple_b200.xyz import poses_to_render
+    torch.manual_seed(0)
+    net = Nerf().cuda()
+    poses = torch.stack(poses_to_render(4, -30, 4)).cuda()
+    rays = ops.generate_rays(poses, 32, 32, 44.4)
+    gt = torch.sigmoid(rays[:, 3:6] * 3)                      # a smooth, learnable colour field
+    tr = Trainer(net, rays, gt, N=32, batch_size=1024, precision="bf16")
+    losses = [tr.step(sync_loss=True) for _ in range(80)]
+    assert np.mean(losses[-10:]) < 0.3 * np.mean(losses[:5]), losses[::10]
+    # the 24 nn.Parameters are views of the flat buffer the optimizer updates
+    assert all(p.data_ptr() >= tr.flat_param.data_ptr() for p in net.parameters())

@@ -113,3 +113,15 @@ def test_compositing_isolated(tag):
                                  G("c_acc"), G("c_w"))
     ref = G("d_outs")
     assert maxabs(d, ref) <= 2e-4 * max(1.0, float(np.max(np.abs(ref))))
+
+
+def test_torch_cpu_port_matches_golden(golden_weights):
+    """The torch-CPU restatement timed as the CPU baseline agrees with the reference's outputs."""
+    import torch
+    from oracle import nerf_oracle_torch as OT
+    g = load_golden("case_render_b1024_n64.npz")
+    P = {k: torch.from_numpy(v) for k, v in golden_weights.items()}
+    with torch.no_grad():
+        rgb, disp, alpha, acc, w = OT.render_nerf(torch.from_numpy(g["rays"]), P, 64, torch.from_numpy(g["u"]))
+    assert maxabs(rgb.numpy(), g["rgb"]) <= 1e-6 and maxabs(w.numpy(), g["weights"]) <= 1e-6
+    assert maxabs(alpha.numpy(), g["alpha"]) <= 1e-6
