@@ -246,7 +246,10 @@ def b200_arm(args, rank, local_rank, world):
             "roofline": {"kernel": "chain_kernel<FwdEpi<false>> (fused posenc+MLP, tcgen05 cta_group::2)", "bound": "tensor", "achieved": achieved, "peak": pk["sustained"],
                          "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "peak_burst": pk["burst"],
                          "frac_burst": achieved / pk["burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                         "kernel_ms": mlp_ms, "flop_per_launch": FLOP_FWD * M, "traffic": None},
+                         "kernel_ms": mlp_ms, "flop_per_launch": FLOP_FWD * M,
+                         "traffic": 792493568 if (H, W, N) == (800, 800, 64) else None,
+                         "traffic_source": "dram__bytes_read+write.sum of one launch, profiles/r1_fwd_chain_v2_ncu_raw.csv "
+                                           "(algorithmic: 655 MB out + 164 MB ts + 15 MB rays)"},
             "clocks": clocks, "outputs_finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:
