@@ -41,6 +41,10 @@ __device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32
   return kb * 16384u + c.rowoff + ((j << 4) ^ c.r7s);
 }
 
+__device__ __forceinline__ void slot_barrier(int slot) {  // the 256 epilogue threads of one slot
+  asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory");
+}
+
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCThreads, 1)
 chain_kernel(const __grid_constant__ typename Epi::Params p) {
@@ -57,7 +61,8 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       mbar_init(bar + kB_WEmpty + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar + kB_Act + 8 * s, 16);  // one elected arrive per epilogue warp: 8 warps x 2 CTAs (leader's copy is used)
+      // inference: one elected arrive per epilogue warp (8 warps x 2 CTAs); training: one per slot per CTA
+      mbar_init(bar + kB_Act + 8 * s, Epi::kBulkStore ? 2 : 16);
       mbar_init(bar + kB_Acc + 8 * s, 1);
     }
     fence_mbar_init();
@@ -91,26 +96,52 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
     uint32_t acc_parity = 0;
     typename Epi::State st;
+    const bool slot_leader = (threadIdx.x & 255) == 0;  // issues this slot's bulk stores (training kernels)
     for (int64_t k = slot; k < my_pt; k += 2) {
       c.tile = 2 * (cid + k * C) + rank;
+      if (Epi::kBulkStore) {  // the previous tile's last tile image must have left shared memory
+        if (slot_leader) tma_bulk_store_wait_read();
+        slot_barrier(slot);
+      }
       Epi::begin_tile(p, st, c);
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(act_remote);
+      if (Epi::kBulkStore) {
+        slot_barrier(slot);
+        if (slot_leader) {
+          Epi::store_tile(p, c, -1);
+          mbar_arrive_cluster(act_remote);
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(act_remote);
+      }
       for (int l = 0; l < Epi::kNumLayers; ++l) {
+        Epi::prefetch(p, st, c, l);  // global loads that do not depend on the accumulator
         mbar_wait(bar + kB_Acc + 8 * slot, acc_parity, 100 + l);
         acc_parity ^= 1;
         tc_fence_after();
+        if (Epi::kBulkStore) {  // A[slot] is about to be overwritten: its bulk store must have read it
+          if (slot_leader) tma_bulk_store_wait_read();
+          slot_barrier(slot);
+        }
         Epi::layer(p, st, c, l);
         tc_fence_before();
-        if (l + 1 < Epi::kNumLayers) {
+        if (Epi::kBulkStore) {
+          fence_proxy_async_smem();
+          slot_barrier(slot);
+          if (slot_leader) {
+            Epi::store_tile(p, c, l);
+            if (l + 1 < Epi::kNumLayers) mbar_arrive_cluster(act_remote);
+          }
+        } else if (l + 1 < Epi::kNumLayers) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(act_remote);
         }
       }
     }
+    if (Epi::kBulkStore && slot_leader) tma_bulk_store_wait_read();
   } else if (warp == kCProducerWarp) {
     // ==================================== weight producer ====================================
     if (lane == 0) {
@@ -281,7 +312,6 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
     }
     const uint32_t o = sw_off(c, kb, j0 + j);
     st_shared_v4(c.a_img + o, w0, w1, w2, w3);
-    if (kSave) *reinterpret_cast<uint4*>(gsave + o) = make_uint4(w0, w1, w2, w3);
   }
 }
 
@@ -306,14 +336,11 @@ __device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8
   }
 }
 
-__device__ __forceinline__ void slot_barrier(int slot) {  // the 256 epilogue threads of one slot
-  asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory");
-}
-
 template <bool kSave>
 struct FwdEpi {
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = true;
+  static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
   static constexpr int kNumLayers = kNumMmaLayers;
   struct State {
     float v[6];
@@ -323,24 +350,33 @@ struct FwdEpi {
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd; }
 
+  __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
+
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
     st.m_raw = c.tile * kTileM + c.r;
     st.row_valid = st.m_raw < p.M;
     load_query_chain(p, st.row_valid ? st.m_raw : p.M - 1, st.v);
     st.sigma = 0.f;
-    uint8_t* gs = kSave ? p.saved + saved_tensor_off(10, p.num_tiles) + (size_t)c.tile * 16384 : nullptr;
     // posx -> E[slot] (K = 64); each half of the slot's threads stores 4 of the 8 16-byte chunks
-    if (c.half == 0) encode_row<kLp, 0, 4>(st.v, c.e_img, c.r, gs);
-    else encode_row<kLp, 4, 8>(st.v, c.e_img, c.r, gs);
+    if (c.half == 0) encode_row<kLp, 0, 4>(st.v, c.e_img, c.r, nullptr);
+    else encode_row<kLp, 4, 8>(st.v, c.e_img, c.r, nullptr);
+  }
+
+  // one thread per slot, after the slot barrier: tile images shared -> global (saved activations)
+  __device__ static void store_tile(const Params& p, const TileCtx& c, int ml) {
+    const int64_t T = p.num_tiles;
+    if (ml == -1) tma_bulk_s2g(p.saved + saved_tensor_off(10, T) + (size_t)c.tile * 16384, c.e_img, 16384);        // posx
+    else if (ml < 9) tma_bulk_s2g(p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536, c.a_img, 65536);    // h0..h7, g
+    else tma_bulk_s2g(p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768, c.a_img, 32768);                  // c1
+    if (ml == 5) tma_bulk_s2g(p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384, c.e_img, 16384);         // posd
   }
 
   __device__ static void layer(const Params& p, State& st, const TileCtx& c, int ml) {
     const int64_t T = p.num_tiles;
     if (ml == 5) {
       // posx has been consumed by the skip layer: the encoding buffer now carries posd (27 -> 64)
-      uint8_t* gs = kSave ? p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384 : nullptr;
-      if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, gs);
-      else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, gs);
+      if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, nullptr);
+      else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, nullptr);
     }
     if (ml < 9) {
       uint8_t* gsave = kSave ? p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536 : nullptr;
@@ -370,9 +406,9 @@ struct FwdEpi {
             rgb[1] = fmaf(x[e], w[128 + 8 * j + e], rgb[1]);
             rgb[2] = fmaf(x[e], w[256 + 8 * j + e], rgb[2]);
           }
-          if (kSave)
-            *reinterpret_cast<uint4*>(gsave + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j))) =
-                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+          if (kSave)  // c1 tile image -> A[slot] K-blocks 0,1 (free after color_fc.0's MMAs), bulk-stored by store_tile
+            st_shared_v4(c.a_img + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j)), pack_bf16x2(x[0], x[1]),
+                         pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
         }
       }
       const uint32_t xaddr = c.e_img + c.r * 16u;
@@ -395,9 +431,11 @@ struct FwdEpi {
 struct DgradEpi {
   using Params = BwdParams;
   static constexpr bool kHasDbg = false;
+  static constexpr bool kBulkStore = true;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   struct State { float4 g; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
+  __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
 
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
     const int64_t T = p.num_tiles;
@@ -422,8 +460,14 @@ struct DgradEpi {
       const uint32_t w0 = mask_pos_bf16x2(pack_bf16x2(x[0], x[1]), cm.x), w1 = mask_pos_bf16x2(pack_bf16x2(x[2], x[3]), cm.y),
                      w2 = mask_pos_bf16x2(pack_bf16x2(x[4], x[5]), cm.z), w3 = mask_pos_bf16x2(pack_bf16x2(x[6], x[7]), cm.w);
       st_shared_v4(c.a_img + o, w0, w1, w2, w3);
-      *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
     }
+  }
+
+  // one thread per slot: delta tile image shared -> global (read back by wgrad)
+  __device__ static void store_tile(const Params& p, const TileCtx& c, int l) {
+    const int64_t T = p.num_tiles;
+    if (l == -1) tma_bulk_s2g(p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768, c.a_img, 32768);   // delta_c1
+    else tma_bulk_s2g(p.dscr + delta_tensor_off(l + 1, T) + (size_t)c.tile * 65536, c.a_img, 65536);
   }
 
   __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
@@ -431,7 +475,6 @@ struct DgradEpi {
     const int64_t T = p.num_tiles;
     // ReLU mask source: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (layers_2 has no activation)
     const uint8_t* himg = (bl >= 2) ? p.saved + saved_tensor_off(9 - bl, T) + (size_t)c.tile * 65536 : nullptr;
-    uint8_t* dsave = p.dscr + delta_tensor_off(bl, T) + (size_t)c.tile * 65536;
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int col0 = c.half * 128 + q * 32;
@@ -459,9 +502,7 @@ struct DgradEpi {
           w0 = mask_pos_bf16x2(w0, hm[j].x); w1 = mask_pos_bf16x2(w1, hm[j].y);
           w2 = mask_pos_bf16x2(w2, hm[j].z); w3 = mask_pos_bf16x2(w3, hm[j].w);
         }
-        const uint32_t o = sw_off(c, kb, j0 + j);
-        if (bl < 9) st_shared_v4(c.a_img + o, w0, w1, w2, w3);
-        *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
+        st_shared_v4(c.a_img + sw_off(c, kb, j0 + j), w0, w1, w2, w3);
       }
     }
   }

@@ -723,10 +723,10 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");
   // 3. sigma / colour heads
   {
-    const int64_t blocks = T < (int64_t)sm_count() * 4 ? T : (int64_t)sm_count() * 4;
-    const int64_t tpb = ceil_div64(T, blocks);
-    mlp_head_grads_kernel<<<(unsigned)ceil_div64(T, tpb), 256, 0, s>>>(sv, d_out, M, T, tpb, G[2 * L_SIGMA], G[2 * L_SIGMA + 1],
-                                                                    G[2 * L_C1], G[2 * L_C1 + 1]);
+    const int64_t want = ceil_div64(T * 8, 8 * 4);  // ~4 (tile, row-group) items per warp
+    const int64_t cap = (int64_t)sm_count() * 4;
+    mlp_head_grads_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, s>>>(
+        sv, d_out, M, T, G[2 * L_SIGMA], G[2 * L_SIGMA + 1], G[2 * L_C1], G[2 * L_C1 + 1]);
     NB_LAUNCH_CHECK("mlp_head_grads_kernel");
   }
   return NB200_OK;

@@ -76,6 +76,17 @@ __device__ __forceinline__ void tma_tensor2d_g2s_2cta(uint32_t dst_smem, const v
       : "memory");
 }
 
+// Contiguous shared -> global copy through the TMA engine (bulk async-group completion).
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk stores of this thread have finished READING shared memory (the source may be reused)
+__device__ __forceinline__ void tma_bulk_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
