@@ -435,7 +435,19 @@ struct DgradEpi {
   static constexpr int kNumLayers = 9;  // bl = 1..9
   struct State { float4 g; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
-  __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
+
+  // The ReLU-mask source of layer l+1 (a 64 KB saved-activation tile written by the forward pass,
+  // long evicted) is pulled into L2 one layer ahead, so the epilogue's 16-byte loads are L2 hits.
+  __device__ static void prefetch(const Params& p, State&, const TileCtx& c, int l) {
+    if ((threadIdx.x & 255) != 0) return;
+    const int bl_next = l + 2;  // layer l+1 has bl = l+2 and masks with tensor 9 - bl
+    if (bl_next >= 2 && bl_next <= 9)
+      tma_prefetch_l2(p.saved + saved_tensor_off(9 - bl_next, p.num_tiles) + (size_t)c.tile * 65536, 65536);
+    if (l == 6) {  // c1 tile of this slot's NEXT 128-row tile (begin_tile masks delta_c1 with it)
+      const int64_t nt = c.tile + 4 * (int64_t)num_clusters_x();
+      if (nt < p.num_tiles) tma_prefetch_l2(p.saved + saved_tensor_off(9, p.num_tiles) + (size_t)nt * 32768, 32768);
+    }
+  }
 
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
     const int64_t T = p.num_tiles;

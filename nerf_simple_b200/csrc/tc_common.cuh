@@ -87,6 +87,11 @@ __device__ __forceinline__ void tma_bulk_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// Ask the TMA engine to pull a contiguous global range into L2 (no shared-memory destination).
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
 // ----------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
