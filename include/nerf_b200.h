@@ -127,6 +127,13 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
                        const void* saved, float* const* grads, void* scratch,
                        size_t scratch_bytes, nb200_stream_t stream);
 
+/* Adam update of one flat parameter buffer.  Replaces torch.optim.Adam(lr=5e-4).step() of
+ * train.py:43,55 for the device-resident trainer (the 24 parameters are views of `param`):
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * `step` is the 1-based step count t.  No weight decay, no amsgrad (the reference uses neither). */
+int nb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    int64_t step, float lr, float beta1, float beta2, float eps, nb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

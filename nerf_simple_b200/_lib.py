@@ -37,6 +37,7 @@ SYMBOLS = {
     "nb200_mlp_scratch_bytes": (_sz, [_i, _i64, _i]),
     "nb200_mlp_forward": (_i, [_i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "nb200_mlp_backward": (_i, [_i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _p]),
 }
 
 _lib = None

@@ -1,6 +1,8 @@
 // Device ray generation and stratified sampling (HBM-bound streaming kernels).
 //   nb200_generate_rays  <- utils/xyz.py:38-52 + utils/rendering.py:129-134
 //   nb200_stratified_ts  <- utils/rendering.py:24-30
+#include <math.h>
+
 #include "common.cuh"
 
 namespace nb200 {
@@ -115,9 +117,50 @@ __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (no weight decay, no amsgrad) over one flat buffer: train.py:43,55.
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                        float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float step_size = lr / bc1;
+  if (i4 + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4), mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * ga[k];
+      va[k] = beta2 * va[k] + (1.f - beta2) * ga[k] * ga[k];
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp; *reinterpret_cast<float4*>(m + i4) = mm; *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      m[i] = beta1 * m[i] + (1.f - beta1) * g[i];
+      v[i] = beta2 * v[i] + (1.f - beta2) * g[i] * g[i];
+      p[i] -= step_size * m[i] / (sqrtf(v[i]) / bc2_sqrt + eps);
+    }
+  }
+}
+
 }  // namespace nb200
 
 extern "C" {
+
+int nb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, float lr,
+                    float beta1, float beta2, float eps, nb200_stream_t stream) {
+  using namespace nb200;
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return NB200_ERR_ARG;
+  if (n == 0) return NB200_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adam_flat_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, as_stream(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+  NB_LAUNCH_CHECK("adam_flat_kernel");
+  return NB200_OK;
+}
 
 int nb200_generate_rays(const float* poses, int P, int H, int W, float f, int64_t ray_begin,
                         int64_t n_rays, float* rays, nb200_stream_t stream) {

@@ -17,6 +17,29 @@ NUM_PARAMS = 595844
 _PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16}
 
 
+def flat_views(flat, shapes):
+    """Views of a flat fp32 buffer for tensors of `shapes`, each starting on a 16-byte boundary (the
+    wgrad kernel flushes aligned rows with vector reductions)."""
+    views, off = [], 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        views.append(flat[off:off + n].view(shp))
+        off += (n + 3) // 4 * 4
+    return views
+
+
+def flat_size(shapes):
+    tot = 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        tot += (n + 3) // 4 * 4
+    return tot
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     _lib.require_cuda(t, name)
     if t.dtype != torch.float32:
@@ -81,12 +104,9 @@ class _MLPFunction(torch.autograd.Function):
         params = ctx.saved_tensors
         dev = d_out.device
         d_out = _f32c(d_out, "d_out")
-        flat = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=dev)
-        views, off = [], 0
-        for p in params:
-            n = p.numel()
-            views.append(flat[off:off + n].view(p.shape))
-            off += n
+        shapes = [tuple(p.shape) for p in params]
+        flat = torch.zeros(flat_size(shapes), dtype=torch.float32, device=dev)
+        views = flat_views(flat, shapes)
         sb = lib.nb200_mlp_scratch_bytes(precision, M, 1)
         scratch = torch.empty(sb, dtype=torch.uint8, device=dev) if sb else None
         rc = lib.nb200_mlp_backward(precision, in_mode, _lib.ptr(in0), _lib.ptr(in1), M, N,

@@ -13,32 +13,27 @@ from __future__ import annotations
 import torch
 
 from . import _lib, config, ops
-from .ops import NUM_PARAMS
+from .ops import NUM_PARAMS, flat_size, flat_views
 
 
 def flatten_parameters(net):
-    """Re-home the 24 parameters of `net` as views of one flat buffer (state_dict unchanged)."""
+    """Re-home the 24 parameters of `net` as views of one flat buffer (state_dict unchanged).  Every
+    tensor starts on a 16-byte boundary, so the buffer has a few padding floats (always zero)."""
     params = list(net.parameters())
-    dev = params[0].device
-    flat = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        n = p.numel()
-        flat[off:off + n].copy_(p.data.reshape(-1))
-        p.data = flat[off:off + n].view(p.shape)
-        off += n
-    assert off == NUM_PARAMS
+    shapes = [tuple(p.shape) for p in params]
+    flat = torch.zeros(flat_size(shapes), dtype=torch.float32, device=params[0].device)
+    for p, v in zip(params, flat_views(flat, shapes)):
+        v.copy_(p.data)
+        p.data = v
     return flat
 
 
 def attach_flat_grad(net, device=None):
     params = list(net.parameters())
-    flat = torch.zeros(NUM_PARAMS, dtype=torch.float32, device=device or params[0].device)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.grad = flat[off:off + n].view(p.shape)
-        off += n
+    shapes = [tuple(p.shape) for p in params]
+    flat = torch.zeros(flat_size(shapes), dtype=torch.float32, device=device or params[0].device)
+    for p, v in zip(params, flat_views(flat, shapes)):
+        p.grad = v
     return flat
 
 
@@ -66,9 +61,11 @@ class Trainer:
         self.flat_grad = attach_flat_grad(net)
         self.params = net.kernel_params()
         self.grads = [p.grad for p in self.params]
-        # train.py:43 Adam(lr=5e-4) with a per-step exponential decay (train.py:39,56-57)
-        self.opt = torch.optim.Adam([torch.nn.Parameter(self.flat_param)], lr=lr, fused=True)
-        self.opt.param_groups[0]["params"][0].grad = self.flat_grad
+        # train.py:43 Adam(lr=5e-4, betas=(0.9,0.999), eps=1e-8) with a per-step exponential lr decay
+        # (train.py:39,56-57), as one kernel over the flat buffer
+        self.lr, self.betas, self.eps, self.t = float(lr), (0.9, 0.999), 1e-8, 0
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.lr_decay = lr_decay
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed)
@@ -116,11 +113,13 @@ class Trainer:
                                           _lib.ptr_array(self.grads), _lib.ptr(self._scratch),
                                           self._scratch.numel(), st), "nb200_mlp_backward")
         allreduce_mean_(self.flat_grad, self.world_size)
-        self.opt.step()
+        self.t += 1
+        _lib.check(lib.nb200_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                       _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), self.t, self.lr, self.betas[0],
+                                       self.betas[1], self.eps, st), "nb200_adam_step")
         self._bump_versions()
-        if self.lr_decay != 1.0:
-            self.opt.param_groups[0]["lr"] *= self.lr_decay
-        self.launches += 9 if self.precision == _lib.BF16 else 60
+        self.lr *= self.lr_decay
+        self.launches += 11 if self.precision == _lib.BF16 else 62   # ts, pack x2, fwd, comp fwd/bwd, dgrad, wgrad, heads, adam
         self.last_loss = loss
         return float(loss) if sync_loss else loss
 

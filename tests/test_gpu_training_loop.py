@@ -93,3 +93,23 @@ def test_device_trainer_converges():
     assert np.mean(losses[-10:]) < 0.3 * np.mean(losses[:5]), losses[::10]
     # the 24 nn.Parameters are views of the flat buffer the optimizer updates
     assert all(p.data_ptr() >= tr.flat_param.data_ptr() for p in net.parameters())
+
+
+def test_flat_adam_matches_torch_adam():
+    """nb200_adam_step == torch.optim.Adam(lr=5e-4) (train.py:43) over several steps."""
+    from nerf_simple_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device="cuda")
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=5e-4)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for t in range(1, 6):
+        g = torch.randn(n, device="cuda") * (0.1 * t)
+        ref.grad = g.clone()
+        opt.step()
+        rc = lib.nb200_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), n, t, 5e-4, 0.9, 0.999, 1e-8,
+                                 _lib.stream_ptr())
+        assert rc == 0
+    assert float((p - ref.detach()).abs().max()) <= 1e-6
