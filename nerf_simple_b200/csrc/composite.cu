@@ -197,8 +197,12 @@ composite_fwd_kernel(const float* __restrict__ outs, const float* __restrict__ t
   }
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// Backward: recompute alpha / transmittance in registers (forward sweep), then a reverse sweep with a
+// warp suffix scan of g_i * w_i (PyTorch's zero-free cumprod backward: reverse_cumsum(grad*out)/input).
+// Branch-free inner loops (selects instead of divergent ifs); resident blocks per SM chosen so the
+// per-sample state of NCH chunks stays in registers.
+template <int NCH, bool kFull>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NCH <= 2) ? 6 : ((NCH <= 4) ? 4 : 2))
 composite_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ ts,
                      const float* __restrict__ dirs, int dirs_mode, const float* __restrict__ d_rgb,
                      const float* __restrict__ d_disp, const float* __restrict__ d_acc,
@@ -208,23 +212,38 @@ composite_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ t
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t ray = warp0; ray < B; ray += nwarps) {
+    float4 o[NCH];
+    float t[NCH], delta[NCH], e[NCH], T[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int idx = c * 32 + lane;
+      const int64_t g = ray * N + ((kFull || idx < N) ? idx : N - 1);
+      o[c] = __ldg(reinterpret_cast<const float4*>(outs) + g);
+      t[c] = __ldg(ts + g);
+    }
     const float norm = dir_norm(dirs, ray, dirs_mode);
-    SampleState st[NCH];
+    const float gr = __ldg(d_rgb + ray * 3), gg = __ldg(d_rgb + ray * 3 + 1), gb = __ldg(d_rgb + ray * 3 + 2);
     float carry = 1.f, sd = 0.f, sa = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      float a, fac;
-      load_sample(outs, ts, ray, N, c * 32 + lane, norm, st[c], a, fac);
-      st[c].T = excl_cumprod(fac, carry, lane);
-      const float w = a * st[c].T;
-      sd = fmaf(w, st[c].t, sd);
+      const int idx = c * 32 + lane;
+      const bool valid = kFull || idx < N;
+      const float nxt = __shfl_down_sync(0xffffffffu, t[c], 1);
+      const float wrap = __shfl_sync(0xffffffffu, t[c + 1 < NCH ? c + 1 : c], 0);
+      const float d = (idx == N - 1) ? 1e10f : __fsub_rn((lane == 31) ? wrap : nxt, t[c]);   // :60-61
+      delta[c] = __fmul_rn(d, norm);                                                         // :62
+      e[c] = valid ? fast_exp(__fmul_rn(-softplus_ref(o[c].w), delta[c])) : 1.f;             // :67
+      const float a = 1.f - e[c];
+      const float fac = valid ? (1.f - a) + 1e-10f : 1.f;                                    // :68
+      T[c] = excl_cumprod(fac, carry, lane);
+      const float w = a * T[c];
+      sd = fmaf(w, t[c], sd);
       sa += w;
     }
-    const float depth = warp_sum(sd), acc = warp_sum(sa);
-    const float gr = __ldg(d_rgb + ray * 3), gg = __ldg(d_rgb + ray * 3 + 1), gb = __ldg(d_rgb + ray * 3 + 2);
-    // disp = 1/max(1e-10, depth/acc)   (:82-83)
+    // disp = 1/max(1e-10, depth/acc)   (:82-83); only when those cotangents exist (not in train.py)
     float g_depth = 0.f, g_acc = d_acc ? __ldg(d_acc + ray) : 0.f;
     if (d_disp) {
+      const float depth = warp_sum(sd), acc = warp_sum(sa);
       const float q = depth / acc;
       const float m = fmaxf(1e-10f, q);
       const float g_q = (q > 1e-10f) ? -__ldg(d_disp + ray) / (m * m) : 0.f;
@@ -235,35 +254,28 @@ composite_bwd_kernel(const float* __restrict__ outs, const float* __restrict__ t
 #pragma unroll
     for (int c = NCH - 1; c >= 0; --c) {
       const int idx = c * 32 + lane;
-      const bool valid = idx < N;
-      const SampleState& s = st[c];
-      const float a = 1.f - s.e;
+      const bool valid = kFull || idx < N;
+      const float a = 1.f - e[c];
       const float fac = (1.f - a) + 1e-10f;
-      const float w = a * s.T;
-      float gw = fmaf(gr, s.o.x, fmaf(gg, s.o.y, gb * s.o.z)) + g_depth * s.t + g_acc;
-      if (d_w && valid) gw += __ldg(d_w + ray * N + idx);
+      const float w = a * T[c];
+      float gw = fmaf(gr, o[c].x, fmaf(gg, o[c].y, gb * o[c].z)) + g_depth * t[c] + g_acc;
+      if (d_w) gw += valid ? __ldg(d_w + ray * N + idx) : 0.f;
       const float x = valid ? gw * w : 0.f;
-      // inclusive suffix scan inside the warp (reverse direction)
-      float p = x;
+      float p = x;  // inclusive suffix scan inside the warp (reverse direction)
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const float v = __shfl_down_sync(0xffffffffu, p, d);
-        if (lane + d < 32) p += v;
+        p += (lane + d < 32) ? v : 0.f;
       }
-      const float S = suffix + (p - x);          // sum_{i>j} gw_i w_i
+      const float S = suffix + (p - x);  // sum_{i>j} gw_i w_i
       suffix += __shfl_sync(0xffffffffu, p, 0);
-      if (valid) {
-        // cumprod backward (zero-free input): reverse_cumsum(grad*out)/input
-        float g_a = gw * s.T - S / fac;
-        if (d_alpha) g_a += __ldg(d_alpha + ray * N + idx);
-        const float g_sp = (g_a * s.e) * s.delta;  // this order keeps 0*1e10 == 0
-        float g_sigma = g_sp;
-        if (!(s.o.w > 20.f)) {
-          const float z = fast_exp(s.o.w);
-          g_sigma = g_sp * z / (z + 1.f);
-        }
+      float g_a = gw * T[c] - __fdividef(S, fac);
+      if (d_alpha) g_a += valid ? __ldg(d_alpha + ray * N + idx) : 0.f;
+      const float g_sp = (g_a * e[c]) * delta[c];  // this order keeps 0*1e10 == 0
+      const float z = fast_exp(fminf(o[c].w, 20.f));
+      const float g_sigma = (o[c].w > 20.f) ? g_sp : g_sp * __fdividef(z, z + 1.f);
+      if (valid)
         reinterpret_cast<float4*>(d_outs)[ray * N + idx] = make_float4(w * gr, w * gg, w * gb, g_sigma);
-      }
     }
   }
 }
@@ -394,9 +406,15 @@ int nb200_composite_backward(const float* outs, const float* ts, const float* di
   if (B == 0) return NB200_OK;
   cudaStream_t s = as_stream(stream);
   const int grid = warp_grid(B), blk = kWarpsPerBlock * 32;
-#define NB_BWD(NCH)                                                                                 \
-  composite_bwd_kernel<NCH><<<grid, blk, 0, s>>>(outs, ts, dirs, dirs_mode, d_rgb, d_disp, d_acc, d_alpha, \
-                                                 d_w, B, N, d_outs)
+#define NB_BWD(NCH)                                                                                          \
+  do {                                                                                                       \
+    if (N == NCH * 32)                                                                                       \
+      composite_bwd_kernel<NCH, true><<<grid, blk, 0, s>>>(outs, ts, dirs, dirs_mode, d_rgb, d_disp, d_acc,  \
+                                                           d_alpha, d_w, B, N, d_outs);                      \
+    else                                                                                                     \
+      composite_bwd_kernel<NCH, false><<<grid, blk, 0, s>>>(outs, ts, dirs, dirs_mode, d_rgb, d_disp, d_acc, \
+                                                            d_alpha, d_w, B, N, d_outs);                     \
+  } while (0)
   if (N <= 32) NB_BWD(1);
   else if (N <= 64) NB_BWD(2);
   else if (N <= 96) NB_BWD(3);
