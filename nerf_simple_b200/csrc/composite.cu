@@ -120,8 +120,14 @@ __device__ __forceinline__ float warp_multi_sum16(float (&v)[16], int lane) {
 // Forward: R rays per warp iteration with every load issued before any math (R*NCH independent
 // 512 B float4 requests + R*NCH 128 B ts requests in flight per warp), so the long dependent
 // softplus/exp/scan chains of one ray overlap the memory latency of the other.
+#ifndef NB_FWD_MB
+#define NB_FWD_MB 6
+#endif
+#ifndef NB_FWD_R64
+#define NB_FWD_R64 2
+#endif
 template <int NCH, int R, bool kFull>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NB_FWD_MB)
 composite_fwd_kernel(const float* __restrict__ outs, const float* __restrict__ ts,
                      const float* __restrict__ dirs, int dirs_mode, int64_t B, int N, float* __restrict__ rgb,
                      float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ alpha_out,
@@ -383,7 +389,7 @@ int nb200_composite_forward(const float* outs, const float* ts, const float* dir
           outs, ts, dirs, dirs_mode, B, N, rgb, disp, acc, alpha, weights);                                  \
   } while (0)
   if (N <= 32) NB_FWD(1, 3);
-  else if (N <= 64) NB_FWD(2, 2);
+  else if (N <= 64) NB_FWD(2, NB_FWD_R64);
   else if (N <= 96) NB_FWD(3, 2);
   else if (N <= 128) NB_FWD(4, 2);
   else if (N <= 192) NB_FWD(6, 1);

@@ -50,15 +50,16 @@ def _render_chunks(net, rays, batch_size, N=128):
     return torch.cat(rgbs), torch.cat(depths)
 
 
-def render_image(net, rg, batch_size=64000, im_idx=0, im_set='val'):
-    """Render image `im_idx` of split `im_set` with N=128 samples/ray; returns CPU tensors
-    (rgb [1,H,W,3], disparity [1,H,W,1], gt [1,H,W,3]).  utils/rendering.py:88-113."""
+def render_image(net, rg, batch_size=64000, im_idx=0, im_set='val', N=128):
+    """Render image `im_idx` of split `im_set` (N=128 samples/ray like the reference; `N` is an
+    extension); returns CPU tensors (rgb [1,H,W,3], disparity [1,H,W,1], gt [1,H,W,3]).
+    utils/rendering.py:88-113."""
     gt_img = rg.samples[im_set][im_idx]['img']
     H, W = gt_img.shape[0], gt_img.shape[1]
     n = H * W
     net = net.cuda()
     rays = rg.rays_dataset[im_set][im_idx * n:(im_idx + 1) * n, :]
-    rgb, depth = _render_chunks(net, rays, batch_size)
+    rgb, depth = _render_chunks(net, rays, batch_size, N=N)
     return rgb.cpu().reshape(1, H, W, 3), depth.cpu().reshape(1, H, W, 1), gt_img.reshape(1, H, W, 3)
 
 
