@@ -127,6 +127,14 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
                        const void* saved, float* const* grads, void* scratch,
                        size_t scratch_bytes, nb200_stream_t stream);
 
+/* EXTENSION (no reference counterpart: hierarchical sampling is "not implemented yet" in the
+ * reference, configs/lego.yaml:7).  Inverse-CDF importance sampler of the NeRF paper (sec. 5.2):
+ * pdf = weights[:,1:-1] + 1e-5 over the mid-point bins of ts [B,Nc], Nf samples per ray drawn with
+ * u (mode 0: dev [B,Nf] supplied; 1: linspace(0,1,Nf); 2: Philox(seed, offset)), merged with the
+ * coarse depths in ascending order into z_all [B, Nc+Nf].  Nc <= 128, Nc+Nf <= 384. */
+int nb200_sample_pdf_merge(const float* ts, const float* weights, const float* u, int mode, uint64_t seed,
+                           uint64_t offset, int64_t B, int Nc, int Nf, float* z_all, nb200_stream_t stream);
+
 /* Adam update of one flat parameter buffer.  Replaces torch.optim.Adam(lr=5e-4).step() of
  * train.py:43,55 for the device-resident trainer (the 24 parameters are views of `param`):
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).

@@ -286,6 +286,31 @@ def train_step_grads(rays, P, N, u, gt, dtype=np.float32):
     return float(loss), grads, rgb
 
 
+# ------------------------------------------------- hierarchical sampling (EXTENSION)
+def sample_pdf_merge(ts, weights, u, dtype=np.float32):
+    """Inverse-CDF importance sampling + sorted merge.  NOT in the reference ("coarse and fine is
+    not implemented yet", configs/lego.yaml:7): restates Mildenhall et al. 2020 sec. 5.2 / the
+    paper's public sample_pdf -- parity unpinned by the reference.
+    ts, weights [B,Nc]; u [B,Nf] in [0,1)  ->  ascending depths [B, Nc+Nf]."""
+    ts = ts.astype(dtype); weights = weights.astype(dtype); u = u.astype(dtype)
+    bins = dtype(0.5) * (ts[:, 1:] + ts[:, :-1])                        # Nc-1 mid points
+    w = weights[:, 1:-1] + dtype(1e-5)                                   # Nc-2 interior weights
+    pdf = w / np.sum(w, axis=-1, keepdims=True)
+    cdf = np.concatenate([np.zeros_like(pdf[:, :1]), np.cumsum(pdf, axis=-1, dtype=dtype)], axis=-1)  # Nc-1
+    B, nb = cdf.shape
+    out = np.empty((B, u.shape[1]), dtype)
+    for b in range(B):
+        inds = np.searchsorted(cdf[b], u[b], side="right")
+        below = np.maximum(0, inds - 1)
+        above = np.minimum(nb - 1, inds)
+        c0, c1 = cdf[b][below], cdf[b][above]
+        denom = c1 - c0
+        denom = np.where(denom < 1e-5, dtype(1), denom)
+        t = (u[b] - c0) / denom
+        out[b] = bins[b][below] + t * (bins[b][above] - bins[b][below])
+    return np.sort(np.concatenate([ts, out], axis=-1), axis=-1).astype(dtype)
+
+
 # ------------------------------------------------------------------ synthetic inputs
 def spherical_to_pose(r, theta_deg, phi_deg):
     """utils/xyz.py:55-81: pose = phi_mat @ theta_mat @ trans_mat (float64, cast by callers)."""

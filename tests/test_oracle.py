@@ -125,3 +125,20 @@ def test_torch_cpu_port_matches_golden(golden_weights):
         rgb, disp, alpha, acc, w = OT.render_nerf(torch.from_numpy(g["rays"]), P, 64, torch.from_numpy(g["u"]))
     assert maxabs(rgb.numpy(), g["rgb"]) <= 1e-6 and maxabs(w.numpy(), g["weights"]) <= 1e-6
     assert maxabs(alpha.numpy(), g["alpha"]) <= 1e-6
+
+
+def test_sample_pdf_extension_properties():
+    """Hierarchical sampler (extension, unpinned): sorted output, contains the coarse depths, and the
+    fine samples concentrate where the coarse weights are."""
+    rng = np.random.default_rng(0)
+    B, Nc, Nf = 16, 64, 128
+    ts = np.sort(2 + 4 * rng.random((B, Nc)), axis=1).astype(np.float32)
+    w = np.full((B, Nc), 1e-4, np.float32)
+    w[:, 30:34] = 1.0                                    # a surface around samples 30..33
+    u = rng.random((B, Nf)).astype(np.float32)
+    z = O.sample_pdf_merge(ts, w, u)
+    assert z.shape == (B, Nc + Nf) and np.all(np.diff(z, axis=1) >= 0)
+    for b in range(B):
+        assert np.all(np.isin(ts[b], z[b]))
+        inside = np.sum((z[b] >= ts[b, 29]) & (z[b] <= ts[b, 35]))
+        assert inside >= 0.9 * Nf
