@@ -168,7 +168,8 @@ def b200_arm(args, rank, local_rank, world):
     net = Nerf().to(dev)                      # random-init weights of the reference architecture
     poses = torch.stack(poses_to_render(4, -30, 30)).to(dev)
     n_poses = poses.shape[0]
-    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision)
+    net_fine = Nerf().to(dev) if args.fine > 0 else None     # --fine 128: hierarchical extension (config 4)
+    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=args.fine)
     n_rays = H * W
     gather_buf = [torch.empty((n_rays, 4), device=dev) for _ in range(world)] if world > 1 else None
 
@@ -229,7 +230,7 @@ def b200_arm(args, rank, local_rank, world):
     # ---- the reference's own host driver, unchanged call: render_image(net, rg, batch_size=16000, ...)
     # (utils/rendering.py:88-113; test.py batch size): CPU ray table in, per-chunk H2D, CPU frame out.
     api_val = None
-    if world == 1:
+    if world == 1 and args.fine == 0:
         from nerf_simple_b200.rendering import render_image
         from nerf_simple_b200 import ops as _ops
 
@@ -257,7 +258,7 @@ def b200_arm(args, rank, local_rank, world):
             "samples_per_sec": value * N,
             "config": {"workload": f"configs[1]: full {H}x{W} novel-view render, {N} samples/ray, spherical-dome path "
                                    f"(poses_to_render(4,-30,30)), one frame per GPU per step",
-                       "H": H, "W": W, "N": N, "rays_per_step_per_gpu": n_rays, "weights": "torch.manual_seed(0); Nerf()",
+                       "H": H, "W": W, "N": N, "N_fine": args.fine, "rays_per_step_per_gpu": n_rays, "weights": "torch.manual_seed(0); Nerf()",
                        "sampler": "device Philox seed 1", "parallelism": f"frames sharded over {world} rank(s) + all_gather of pixels",
                        "l2": "inputs larger than L2: 655 MB of per-sample (r,g,b,sigma) + 164 MB of ts per frame"},
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 64,
@@ -381,6 +382,7 @@ def main():
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fine", type=int, default=0, help="extension: fine samples per ray (64 coarse + N fine)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -20,8 +20,9 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class FrameRenderer:
-    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None):
+    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None, net_fine=None, Nf=0):
         self.net, self.H, self.W, self.f, self.N = net, int(H), int(W), float(f), int(N)
+        self.net_fine, self.Nf = net_fine, int(Nf)   # hierarchical extension: N coarse + Nf fine samples
         self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
         self.precision = precision
         self.device = next(net.parameters()).device
@@ -44,9 +45,20 @@ class FrameRenderer:
             if time_mlp:
                 e1.record()
                 self.mlp_events.append((e0, e1))
-            rgb, disp, _ = ops.composite_apply(out.view(n_rays, self.N, 4), ts, rays, dirs_mode=1,
-                                               want_alpha_weights=False)
-            self.launches += 4
+            if self.net_fine is None:
+                rgb, disp, _ = ops.composite_apply(out.view(n_rays, self.N, 4), ts, rays, dirs_mode=1,
+                                                   want_alpha_weights=False)
+                self.launches += 4
+                return rgb.clamp_(0.0, 1.0), disp
+            # hierarchical extension: importance-resample Nf depths from the coarse weights, fine pass
+            from .hierarchical import sample_pdf_merge
+            w = ops.composite_apply(out.view(n_rays, self.N, 4), ts, rays, dirs_mode=1)[4]
+            z = sample_pdf_merge(ts, w, self.Nf, seed=self.seed + 7919, offset=self._offset)
+            self._offset += (n_rays * self.Nf + 3) // 4
+            NA = self.N + self.Nf
+            out_f = ops.mlp_apply(self.net_fine, _lib.IN_RAYS, rays, z, NA, precision=self.precision)
+            rgb, disp, _ = ops.composite_apply(out_f.view(n_rays, NA, 4), z, rays, dirs_mode=1, want_alpha_weights=False)
+            self.launches += 7
             return rgb.clamp_(0.0, 1.0), disp
 
     def render_frame(self, poses_dev, idx=0, time_mlp=False):
