@@ -376,8 +376,9 @@ int nb200_composite_forward(const float* outs, const float* ts, const float* dir
                             float* rgb, float* disp, float* acc, float* alpha, float* weights,
                             nb200_stream_t stream) {
   using namespace nb200;
-  if (!outs || !ts || !dirs || !rgb || !disp || !acc || B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
-  if (B == 0) return NB200_OK;
+  if (B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
+  if (B == 0) return NB200_OK;  // empty batch: pointers may be null
+  if (!outs || !ts || !dirs || !rgb || !disp || !acc) return NB200_ERR_ARG;
   cudaStream_t s = as_stream(stream);
 #define NB_FWD(NCH, R)                                                                                       \
   do {                                                                                                       \
@@ -408,8 +409,9 @@ int nb200_composite_backward(const float* outs, const float* ts, const float* di
                              const float* d_alpha, const float* d_w, int64_t B, int N,
                              float* d_outs, nb200_stream_t stream) {
   using namespace nb200;
-  if (!outs || !ts || !dirs || !d_rgb || !d_outs || B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
+  if (B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
   if (B == 0) return NB200_OK;
+  if (!outs || !ts || !dirs || !d_rgb || !d_outs) return NB200_ERR_ARG;
   cudaStream_t s = as_stream(stream);
   const int grid = warp_grid(B), blk = kWarpsPerBlock * 32;
 #define NB_BWD(NCH)                                                                                          \

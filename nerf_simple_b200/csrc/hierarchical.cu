@@ -115,10 +115,10 @@ sample_pdf_merge_kernel(const float* __restrict__ ts, const float* __restrict__ 
 extern "C" int nb200_sample_pdf_merge(const float* ts, const float* weights, const float* u, int mode, uint64_t seed,
                                       uint64_t offset, int64_t B, int Nc, int Nf, float* z_all, nb200_stream_t stream) {
   using namespace nb200;
-  if (!ts || !weights || !z_all || B < 0 || Nc < 3 || Nf < 1 || mode < 0 || mode > 2) return NB200_ERR_ARG;
-  if (mode == 0 && !u) return NB200_ERR_ARG;
+  if (B < 0 || Nc < 3 || Nf < 1 || mode < 0 || mode > 2) return NB200_ERR_ARG;
   if (Nc > kHsMaxNc || Nc + Nf > kHsMaxAll) return NB200_ERR_UNSUPPORTED;
   if (B == 0) return NB200_OK;
+  if (!ts || !weights || !z_all || (mode == 0 && !u)) return NB200_ERR_ARG;
   const int64_t blocks = ceil_div64(B, kHsWarps);
   const int64_t cap = (int64_t)sm_count() * 16;
   sample_pdf_merge_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kHsWarps * 32, 0, as_stream(stream)>>>(

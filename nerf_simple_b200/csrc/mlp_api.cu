@@ -50,8 +50,9 @@ size_t nb200_mlp_scratch_bytes(int precision, int64_t M, int train) {
 static int check_common(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N) {
   if (precision != NB200_FP32 && precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;
   if (in_mode != NB200_IN_POINTS && in_mode != NB200_IN_RAYS) return NB200_ERR_ARG;
-  if (!in0 || M < 0) return NB200_ERR_ARG;
-  if (in_mode == NB200_IN_RAYS && (!in1 || N < 1 || M % N != 0)) return NB200_ERR_ARG;
+  if (M < 0) return NB200_ERR_ARG;
+  if (in_mode == NB200_IN_RAYS && (N < 1 || M % N != 0)) return NB200_ERR_ARG;
+  if (M > 0 && (!in0 || (in_mode == NB200_IN_RAYS && !in1))) return NB200_ERR_ARG;  // empty batch: null ok
   return NB200_OK;
 }
 
@@ -60,8 +61,8 @@ int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float*
                       void* scratch, size_t scratch_bytes, nb200_stream_t stream) {
   int rc = check_common(precision, in_mode, in0, in1, M, N);
   if (rc != NB200_OK) return rc;
-  if (!out) return NB200_ERR_ARG;
   if (M == 0) return NB200_OK;
+  if (!out) return NB200_ERR_ARG;
   if (precision == NB200_FP32) {
     if (!params) return NB200_ERR_ARG;
     return nb200::fp32_forward(in_mode, in0, in1, M, N, params, out, saved, scratch, scratch_bytes,
@@ -78,10 +79,11 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
                        nb200_stream_t stream) {
   int rc = check_common(precision, in_mode, in0, in1, M, N);
   if (rc != NB200_OK) return rc;
-  if (!d_out || !saved || !grads) return NB200_ERR_ARG;
+  if (!grads) return NB200_ERR_ARG;
   for (int i = 0; i < 24; ++i)
     if (!grads[i]) return NB200_ERR_ARG;
-  if (M == 0) return NB200_OK;
+  if (M == 0) return NB200_OK;  // gradients are accumulated into: nothing to add
+  if (!d_out || !saved) return NB200_ERR_ARG;
   if (precision == NB200_FP32) {
     if (!params) return NB200_ERR_ARG;
     return nb200::fp32_backward(M, params, d_out, saved, grads, scratch, scratch_bytes,

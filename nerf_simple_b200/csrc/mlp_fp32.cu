@@ -399,8 +399,9 @@ int fp32_backward(int64_t M, const float* const* P, const float* d_out, const vo
 extern "C" int nb200_positional_encoding(const float* v, int64_t M, int Lp, int Ld, float* posx,
                                          float* posd, nb200_stream_t stream) {
   using namespace nb200;
-  if (!v || !posx || !posd || M < 0 || Lp < 0 || Ld < 0 || Lp > 24 || Ld > 24) return NB200_ERR_ARG;
+  if (M < 0 || Lp < 0 || Ld < 0 || Lp > 24 || Ld > 24) return NB200_ERR_ARG;
   if (M == 0) return NB200_OK;
+  if (!v || !posx || !posd) return NB200_ERR_ARG;
   PointSrc src = {NB200_IN_POINTS, v, nullptr, 1};
   return posenc_launch(src, M, Lp, Ld, posx, 3 + 6 * Lp, posd, 3 + 6 * Ld, as_stream(stream));
 }

@@ -1,20 +1,12 @@
 // NB200_BF16 precision: fused positional-encoding + NeRF MLP on tcgen05 / TMEM (sm_100a).
 //   forward  <- utils/xyz.py:16-36 + utils/nets.py:34-43 (+ utils/rendering.py:31-40 in rays mode)
+//   backward <- autograd of the same (parameter gradients only)
 //
-// One persistent CTA per SM.  A CTA keeps TWO 128-sample tiles in flight (slots 0/1): while the
-// epilogue warps of one slot turn the fp32 accumulator of layer l (TMEM) into the bf16 A operand
-// of layer l+1 (shared memory, never HBM), the single MMA-issuing thread runs layer l of the other
-// slot.  Weights are streamed per layer from the L2-resident packed image (pre-swizzled bf16
-// UMMA operand slabs) by a TMA bulk-copy producer warp through a 2-stage ring.
-//
-//   warps 0-3 : encoder + epilogue of slot 0   (thread i <-> sample row i <-> TMEM lane i)
-//   warps 4-7 : encoder + epilogue of slot 1
-//   warp  8   : weight producer (cp.async.bulk -> mbarrier complete_tx)
-//   warp  9   : TMEM allocator + MMA issuer (tcgen05.mma, cta_group::1, M=128, N=256/128, K=16)
-//
-// Shared memory (bytes, 1024-aligned):  A[2] 2x64 KB (128 x 256 bf16, 4 K-blocks of 128 B rows,
-// SWIZZLE_128B) | E[2] 2x16 KB (encoded input: posx 63->64, later posd 27->32) | W ring 2x32 KB.
-// TMEM: 512 columns = two 128x256 fp32 accumulators.
+// This file owns the packed weight image (pre-swizzled bf16 UMMA operand slabs + fp32 tail), the
+// saved-tensor layout and the host entry points.  The kernels live in
+//   mlp_chain.cuh  : chain_kernel<FwdEpi> / chain_kernel<DgradEpi> -- persistent 2-CTA clusters,
+//                    tcgen05.mma.cta_group::2, two tiles in flight per CTA, weights by tensor-map TMA
+//   mlp_tc_bwd.cuh : wgrad (MN-major UMMA operands, dW resident in TMEM) and the head gradients
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -177,15 +169,9 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(ParamPtrs P, float* __res
   f[i] = v;
 }
 
-// ------------------------------------------------------------------------ forward kernel
-constexpr int kTileM = 128;
-constexpr uint32_t kABytes = 65536, kEBytes = 16384, kWStageBytes = 32768;
-constexpr int kNumWStages = 2;
-constexpr uint32_t kSmemA = 0, kSmemE = 2 * kABytes, kSmemW = kSmemE + 2 * kEBytes,
-                   kSmemBar = kSmemW + kNumWStages * kWStageBytes;  // 229376
-constexpr uint32_t kSmemTotal = kSmemBar + 128;
-constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;  // slack for manual 1024 B alignment
-constexpr int kFwdThreads = 320;
+// ------------------------------------------------------------------------- tile geometry
+constexpr int kTileM = 128;                               // samples per tile (= TMEM lanes)
+constexpr uint32_t kABytes = 65536, kEBytes = 16384;      // activation tile 128x256 bf16, encoding tile 128x64 bf16
 
 // saved activations (training): tensors 0..7 = h0..h7, 8 = g (256 cols, 64 KB per tile), 9 = c1
 // (128 cols, 32 KB per tile), 10 = posx (64 cols, 16 KB), 11 = posd (32 of 64 cols, 16 KB).  Every
@@ -198,37 +184,6 @@ __host__ __device__ __forceinline__ size_t saved_tensor_off(int t, int64_t num_t
 }
 __host__ __device__ __forceinline__ size_t saved_tile_bytes(int t) {
   return t < 9 ? 65536 : (t == 9 ? 32768 : 16384);
-}
-
-struct FwdParams {
-  int in_mode;
-  const float* in0;
-  const float* in1;
-  int64_t M;
-  int N;
-  const uint8_t* packed;
-  float* out;
-  uint8_t* saved;  // null for inference
-  int64_t num_tiles;
-};
-
-__device__ __forceinline__ void load_query_tc(const FwdParams& p, int64_t m, float v[6]) {
-  if (p.in_mode == NB200_IN_POINTS) {
-    const float2* q = reinterpret_cast<const float2*>(p.in0 + m * 6);
-    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
-  } else {
-    const int64_t ray = m / p.N;
-    const float2* q = reinterpret_cast<const float2*>(p.in0 + ray * 6);
-    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    const float t = __ldg(p.in1 + m);
-    const float dx = b.y, dy = c.x, dz = c.y;
-    v[0] = __fadd_rn(a.x, __fmul_rn(dx, t));   // utils/rendering.py:34-36 (d un-normalised)
-    v[1] = __fadd_rn(a.y, __fmul_rn(dy, t));
-    v[2] = __fadd_rn(b.x, __fmul_rn(dz, t));
-    const float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));   // :37
-    v[3] = dx * inv; v[4] = dy * inv; v[5] = dz * inv;
-  }
 }
 
 // Encode 3 coordinates with L levels into the bf16 operand row `r` of a SWIZZLE_128B image:
@@ -264,243 +219,6 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
   }
 }
 
-template <bool kSave>
-__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_tc_kernel(const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kSmemBar;
-  // barriers: w_full[2] @0, w_empty[2] @16, act_ready[2] @32, acc_full[2] @48, tmem ptr @64
-  const uint32_t bar_wfull = bar_base, bar_wempty = bar_base + 16, bar_act = bar_base + 32,
-                 bar_acc = bar_base + 48, tmem_slot = bar_base + 64;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumWStages; ++i) {
-      mbar_init(bar_wfull + 8 * i, 1);
-      mbar_init(bar_wempty + 8 * i, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_act + 8 * s, 128);
-      mbar_init(bar_acc + 8 * s, 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int64_t T = p.num_tiles;
-  const int64_t G = gridDim.x;
-  const int64_t my_tiles = (blockIdx.x < T) ? (T - blockIdx.x + G - 1) / G : 0;
-  const float* f32sec = reinterpret_cast<const float*>(p.packed + c_layout.f32_off);
-
-  if (warp < 8) {
-    // ===================== encoder + epilogue warpgroup of one slot =====================
-    const int slot = warp >> 2;
-    const uint32_t r = threadIdx.x & 127;  // row in tile == TMEM lane
-    const uint32_t a_img = smem_base + kSmemA + slot * kABytes;
-    const uint32_t e_img = smem_base + kSmemE + slot * kEBytes;
-    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
-    uint32_t acc_parity = 0;
-    for (int64_t k = slot; k < my_tiles; k += 2) {
-      const int64_t tile = blockIdx.x + k * G;
-      const int64_t m_raw = tile * kTileM + r;
-      const bool row_valid = m_raw < p.M;
-      const int64_t m = row_valid ? m_raw : p.M - 1;
-      float v[6];
-      load_query_tc(p, m, v);
-      encode_row<kLp, 0, 8>(v, e_img, r,   // posx -> E[slot], K = 64
-                         kSave ? p.saved + saved_tensor_off(10, T) + (size_t)tile * 16384 : nullptr);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bar_act + 8 * slot);
-      float sigma = 0.f;
-      for (int ml = 0; ml < kNumMmaLayers; ++ml) {
-        mbar_wait(bar_acc + 8 * slot, acc_parity, 100 + ml);
-        acc_parity ^= 1;
-        tc_fence_after();
-        const float* bias = f32sec + kF32Bias + ml * 256;
-        if (ml == 5) {
-          // posx has been consumed by the skip layer: the encoding buffer now carries posd
-          encode_row<kLd, 0, 8>(v + 3, e_img, r,   // cols 27..63 zero: wgrad reads the image with N = 64
-                             kSave ? p.saved + saved_tensor_off(11, T) + (size_t)tile * 16384 : nullptr);
-        }
-        if (ml < 9) {
-          const bool relu = (ml != 8);  // layers_2 has no activation (utils/nets.py:28,41)
-          uint8_t* gsave = nullptr;
-          if (kSave) gsave = p.saved + saved_tensor_off(ml, T) + (size_t)tile * 65536;
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {  // 8 chunks of 32 accumulator columns
-            uint32_t acc[32];
-            tmem_ld32(t_lane + c * 32, acc);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + q);
-              x[4 * q] = __uint_as_float(acc[4 * q]) + b4.x;
-              x[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
-              x[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z;
-              x[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
-            }
-            if (relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-            }
-            if (ml == 7) {  // sigma head reads the layers_1 output (utils/nets.py:40)
-              const float* ws = f32sec + kF32WSig + c * 32;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + q);
-                sigma = fmaf(x[4 * q], w4.x, sigma);
-                sigma = fmaf(x[4 * q + 1], w4.y, sigma);
-                sigma = fmaf(x[4 * q + 2], w4.z, sigma);
-                sigma = fmaf(x[4 * q + 3], w4.w, sigma);
-              }
-            }
-            const uint32_t kb = c >> 1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t j = (c & 1) * 4 + q;
-              const uint32_t w0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), w1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                             w2 = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), w3 = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
-              const uint32_t o = kb * 16384u + sw128_off(r, j);
-              st_shared_v4(a_img + o, w0, w1, w2, w3);
-              if (kSave) *reinterpret_cast<uint4*>(gsave + o) = make_uint4(w0, w1, w2, w3);
-            }
-          }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_act + 8 * slot);
-        } else {
-          // color_fc.0 epilogue (128 columns) + color_fc.2 (128 -> 3) on CUDA cores
-          uint8_t* gsave = nullptr;
-          if (kSave) gsave = p.saved + saved_tensor_off(9, T) + (size_t)tile * 32768;
-          float rgb[3] = {0.f, 0.f, 0.f};
-          const float* wc1 = f32sec + kF32WC1;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t acc[32];
-            tmem_ld32(t_lane + c * 32, acc);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + q);
-              x[4 * q] = fmaxf(__uint_as_float(acc[4 * q]) + b4.x, 0.f);
-              x[4 * q + 1] = fmaxf(__uint_as_float(acc[4 * q + 1]) + b4.y, 0.f);
-              x[4 * q + 2] = fmaxf(__uint_as_float(acc[4 * q + 2]) + b4.z, 0.f);
-              x[4 * q + 3] = fmaxf(__uint_as_float(acc[4 * q + 3]) + b4.w, 0.f);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wc1 + ch * 128 + c * 32) + q);
-                rgb[ch] = fmaf(x[4 * q], w4.x, rgb[ch]);
-                rgb[ch] = fmaf(x[4 * q + 1], w4.y, rgb[ch]);
-                rgb[ch] = fmaf(x[4 * q + 2], w4.z, rgb[ch]);
-                rgb[ch] = fmaf(x[4 * q + 3], w4.w, rgb[ch]);
-              }
-            }
-            if (kSave) {
-              const uint32_t kb = c >> 1;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t j = (c & 1) * 4 + q;
-                *reinterpret_cast<uint4*>(gsave + kb * 16384u + sw128_off(r, j)) =
-                    make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                               pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
-              }
-            }
-          }
-          if (row_valid) {
-            const float bs = __ldg(f32sec + kF32BSig);
-            reinterpret_cast<float4*>(p.out)[m_raw] =
-                make_float4(rgb[0] + __ldg(f32sec + kF32BC1), rgb[1] + __ldg(f32sec + kF32BC1 + 1),
-                            rgb[2] + __ldg(f32sec + kF32BC1 + 2), sigma + bs);  // (r,g,b,sigma) :43
-          }
-          tc_fence_before();  // TMEM reads of this tile are ordered before the next act_ready arrive
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ================================ weight producer ================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      const int nslabs = c_layout.num_fwd;
-      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
-        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
-        int s0 = 0;
-        for (int ml = 0; ml < kNumMmaLayers; ++ml) {
-          int s1 = s0;
-          while (!c_layout.fwd[s1].last) ++s1;
-          for (int slot = 0; slot < nslots; ++slot) {
-            for (int s = s0; s <= s1; ++s) {
-              const uint32_t off = c_layout.fwd[s].off, bytes = c_layout.fwd[s].bytes;
-              mbar_wait(bar_wempty + 8 * stage, phase ^ 1, 200);
-              mbar_arrive_expect_tx(bar_wfull + 8 * stage, bytes);
-              tma_bulk_g2s(smem_base + kSmemW + stage * kWStageBytes, p.packed + off, bytes,
-                           bar_wfull + 8 * stage);
-              if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
-            }
-          }
-          s0 = s1 + 1;
-        }
-      }
-      (void)nslabs;
-    }
-  } else {
-    // ================================== MMA issuer ==================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t act_parity[2] = {0, 0};
-      const uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0);
-      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
-        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
-        int s0 = 0;
-        for (int ml = 0; ml < kNumMmaLayers; ++ml) {
-          int s1 = s0;
-          while (!c_layout.fwd[s1].last) ++s1;
-          for (int slot = 0; slot < nslots; ++slot) {
-            mbar_wait(bar_act + 8 * slot, act_parity[slot], 300 + ml);
-            act_parity[slot] ^= 1;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-            for (int s = s0; s <= s1; ++s) {
-              const SlabDesc& d = c_layout.fwd[s];
-              mbar_wait(bar_wfull + 8 * stage, phase, 400);
-              tc_fence_after();
-              const uint32_t a_addr = d.src ? (smem_base + kSmemE + slot * kEBytes)
-                                            : (smem_base + kSmemA + slot * kABytes + d.kb * 16384u);
-              const uint32_t b_addr = smem_base + kSmemW + stage * kWStageBytes;
-              const uint32_t idesc = (d.n == 256) ? idesc256 : idesc128;
-              const int ksteps = d.ksteps;
-              for (int kk = 0; kk < ksteps; ++kk) {
-                umma_bf16(d_tmem, umma_smem_desc(a_addr + kk * 32, 16, 1024),
-                          umma_smem_desc(b_addr + kk * 32, 16, 1024), idesc, (d.first && kk == 0) ? 0u : 1u);
-              }
-              umma_commit(bar_wempty + 8 * stage);  // slab may be overwritten once these MMAs retire
-              if (++stage == kNumWStages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(bar_acc + 8 * slot);  // accumulator of (slot, layer) complete
-          }
-          s0 = s1 + 1;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 #include "mlp_tc_bwd.cuh"
 #include "mlp_chain.cuh"
 
@@ -529,12 +247,6 @@ static int check_arch() {
   if (arch == 0) arch = nb200_device_arch();
   if (arch < 0) return NB200_ERR_CUDA;
   return (arch / 10 == 10) ? NB200_OK : NB200_ERR_ARCH;
-}
-
-static bool use_v1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NB200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
 }
 
 // biases / head weights of the net being run go to the constant bank (stream-ordered D2D copy)
@@ -600,10 +312,6 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   NB_TRY_RC(ensure_layout());
   static bool attr_set = false;
   if (!attr_set) {
-    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kSmemLaunch));
-    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -611,21 +319,6 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
     attr_set = true;
   }
   const int64_t T = ceil_div64(M, kTileM);
-  if (use_v1()) {
-    FwdParams p;
-    p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
-    p.packed = reinterpret_cast<const uint8_t*>(packed);
-    p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
-    p.num_tiles = T;
-    const int64_t want = (p.num_tiles + 1) / 2;  // two tiles per CTA keep the ping-pong busy
-    const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
-    if (saved)
-      mlp_fwd_tc_kernel<true><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
-    else
-      mlp_fwd_tc_kernel<false><<<grid, kFwdThreads, kSmemLaunch, s>>>(p);
-    NB_LAUNCH_CHECK("mlp_fwd_tc_kernel");
-    return NB200_OK;
-  }
   NB_TRY_RC(upload_consts(packed, s));
   const TmapPair* tm = nullptr;
   NB_TRY_RC(get_tmaps(packed, &tm));
@@ -662,7 +355,6 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   if (!scratch || scratch_bytes < tc_scratch_bytes(M, 1)) return NB200_ERR_WORKSPACE;
   static bool attr_set = false;
   if (!attr_set) {
-    NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
     attr_set = true;
@@ -675,12 +367,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   bp.dbg = 0;
   bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
   bp.d_out = d_out; bp.dscr = ds;
-  if (use_v1()) {
-    const int64_t want = (T + 1) / 2;
-    const int grid = (int)(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
-    mlp_dgrad_tc_kernel<<<grid, kFwdThreads, kSmemLaunch, s>>>(bp);
-    NB_LAUNCH_CHECK("mlp_dgrad_tc_kernel");
-  } else {
+  {
     NB_TRY_RC(upload_consts(packed, s));
     const TmapPair* tm = nullptr;
     NB_TRY_RC(get_tmaps(packed, &tm));

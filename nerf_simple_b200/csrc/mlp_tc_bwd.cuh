@@ -1,7 +1,7 @@
 // Backward of the fused MLP on tcgen05 (included inside namespace nb200 by mlp_tc.cu).
 //
-//   mlp_dgrad_tc_kernel : fused delta chain.  Same ping-pong structure as the forward kernel; per
-//       128-sample tile it walks color_fc.0 -> layers_2 -> layers_1 -> skip -> layers_0 backwards,
+//   chain_kernel<DgradEpi> (mlp_chain.cuh): fused delta chain.  Same skeleton as the forward kernel;
+//       per 128-sample tile it walks color_fc.0 -> layers_2 -> layers_1 -> skip -> layers_0 backwards,
 //       delta_in = (delta_out @ W) * relu'(saved activation), each delta kept in shared memory as
 //       the A operand of the next MMA and written once to HBM (bf16 tile image) for wgrad.
 //   mlp_wgrad_tc_kernel : dW = delta^T @ activation for the 12 (delta, input) pairs.  Both operands
@@ -28,201 +28,12 @@ struct BwdParams {
   uint8_t* dscr;       // delta scratch
 };
 
-constexpr int kBwdWStages = 3;
-constexpr uint32_t kBwdSmemW = 2 * kABytes, kBwdSmemBar = kBwdSmemW + kBwdWStages * kWStageBytes;  // 229376
-static_assert(kBwdSmemBar == kSmemBar, "dgrad kernel reuses the forward shared-memory budget");
-
 __device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t v, uint32_t h) {
   // ReLU backward on a packed pair: v * (h > 0), two instructions (HSET2.BF16.GT + HMUL2.BF16)
   const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&h);
   const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(&v);
   const __nv_bfloat162 r = __hmul2(vv, __hgt2(hv, __float2bfloat162_rn(0.f)));
   return *reinterpret_cast<const uint32_t*>(&r);
-}
-
-__global__ void __launch_bounds__(kFwdThreads, 1) mlp_dgrad_tc_kernel(const BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kBwdSmemBar;
-  const uint32_t bar_wfull = bar_base, bar_wempty = bar_base + 24, bar_act = bar_base + 48,
-                 bar_acc = bar_base + 64, tmem_slot = bar_base + 80;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kBwdWStages; ++i) {
-      mbar_init(bar_wfull + 8 * i, 1);
-      mbar_init(bar_wempty + 8 * i, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_act + 8 * s, 128);
-      mbar_init(bar_acc + 8 * s, 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int64_t T = p.num_tiles, G = gridDim.x;
-  const int64_t my_tiles = (blockIdx.x < T) ? (T - blockIdx.x + G - 1) / G : 0;
-  const float* f32sec = reinterpret_cast<const float*>(p.packed + c_layout.f32_off);
-
-  if (warp < 8) {
-    const int slot = warp >> 2;
-    const uint32_t r = threadIdx.x & 127;
-    const uint32_t a_img = smem_base + kSmemA + slot * kABytes;
-    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
-    uint32_t acc_parity = 0;
-    for (int64_t k = slot; k < my_tiles; k += 2) {
-      const int64_t tile = blockIdx.x + k * G;
-      const int64_t m_raw = tile * kTileM + r;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M carry zero gradient
-      if (m_raw < p.M) g = __ldg(reinterpret_cast<const float4*>(p.d_out) + m_raw);
-      {
-        // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
-        const uint8_t* c1img = p.saved + saved_tensor_off(9, T) + (size_t)tile * 32768;
-        uint8_t* dsave = p.dscr + delta_tensor_off(0, T) + (size_t)tile * 32768;
-        const float* wc1 = f32sec + kF32WC1;
-#pragma unroll 1
-        for (int q = 0; q < 16; ++q) {
-          const uint32_t o = (uint32_t)(q >> 3) * 16384u + sw128_off(r, q & 7);
-          const uint4 cm = __ldg(reinterpret_cast<const uint4*>(c1img + o));
-          float x[8];
-#pragma unroll
-          for (int e = 0; e < 8; e += 4) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc1 + q * 8 + e));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc1 + 128 + q * 8 + e));
-            const float4 w2 = __ldg(reinterpret_cast<const float4*>(wc1 + 256 + q * 8 + e));
-            x[e] = fmaf(g.z, w2.x, fmaf(g.y, w1.x, g.x * w0.x));
-            x[e + 1] = fmaf(g.z, w2.y, fmaf(g.y, w1.y, g.x * w0.y));
-            x[e + 2] = fmaf(g.z, w2.z, fmaf(g.y, w1.z, g.x * w0.z));
-            x[e + 3] = fmaf(g.z, w2.w, fmaf(g.y, w1.w, g.x * w0.w));
-          }
-          const uint32_t w0 = mask_pos_bf16x2(pack_bf16x2(x[0], x[1]), cm.x), w1 = mask_pos_bf16x2(pack_bf16x2(x[2], x[3]), cm.y),
-                         w2 = mask_pos_bf16x2(pack_bf16x2(x[4], x[5]), cm.z), w3 = mask_pos_bf16x2(pack_bf16x2(x[6], x[7]), cm.w);
-          st_shared_v4(a_img + o, w0, w1, w2, w3);
-          *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bar_act + 8 * slot);
-      for (int bl = 1; bl <= 9; ++bl) {
-        mbar_wait(bar_acc + 8 * slot, acc_parity, 500 + bl);
-        acc_parity ^= 1;
-        tc_fence_after();
-        // ReLU mask source: bl=2 -> h7, ..., bl=9 -> h0; layers_2 (bl=1 output delta_g) has no activation
-        const uint8_t* himg = (bl >= 2) ? p.saved + saved_tensor_off(9 - bl, T) + (size_t)tile * 65536 : nullptr;
-        uint8_t* dsave = p.dscr + delta_tensor_off(bl, T) + (size_t)tile * 65536;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          uint32_t acc[32];
-          tmem_ld32(t_lane + c * 32, acc);
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(acc[i]);
-          if (bl == 2) {  // sigma head reads h7 too: + d_sigma * w_sigma   (utils/nets.py:40)
-            const float* ws = f32sec + kF32WSig + c * 32;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws) + q);
-              x[4 * q] = fmaf(g.w, w4.x, x[4 * q]);
-              x[4 * q + 1] = fmaf(g.w, w4.y, x[4 * q + 1]);
-              x[4 * q + 2] = fmaf(g.w, w4.z, x[4 * q + 2]);
-              x[4 * q + 3] = fmaf(g.w, w4.w, x[4 * q + 3]);
-            }
-          }
-          const uint32_t kb = c >> 1;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t o = kb * 16384u + sw128_off(r, (c & 1) * 4 + q);
-            uint32_t w0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), w1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                     w2 = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), w3 = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
-            if (himg) {
-              const uint4 hm = __ldg(reinterpret_cast<const uint4*>(himg + o));
-              w0 = mask_pos_bf16x2(w0, hm.x); w1 = mask_pos_bf16x2(w1, hm.y);
-              w2 = mask_pos_bf16x2(w2, hm.z); w3 = mask_pos_bf16x2(w3, hm.w);
-            }
-            if (bl < 9) st_shared_v4(a_img + o, w0, w1, w2, w3);
-            *reinterpret_cast<uint4*>(dsave + o) = make_uint4(w0, w1, w2, w3);
-          }
-        }
-        if (bl < 9) {
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_act + 8 * slot);
-        } else {
-          tc_fence_before();
-        }
-      }
-    }
-  } else if (warp == 8) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
-        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
-        int s0 = 0;
-        for (int bl = 1; bl <= 9; ++bl) {
-          int s1 = s0;
-          while (!c_layout.bwd[s1].last) ++s1;
-          for (int slot = 0; slot < nslots; ++slot) {
-            for (int s = s0; s <= s1; ++s) {
-              mbar_wait(bar_wempty + 8 * stage, phase ^ 1, 600);
-              mbar_arrive_expect_tx(bar_wfull + 8 * stage, c_layout.bwd[s].bytes);
-              tma_bulk_g2s(smem_base + kBwdSmemW + stage * kWStageBytes, p.packed + c_layout.bwd[s].off,
-                           c_layout.bwd[s].bytes, bar_wfull + 8 * stage);
-              if (++stage == kBwdWStages) { stage = 0; phase ^= 1; }
-            }
-          }
-          s0 = s1 + 1;
-        }
-      }
-    }
-  } else {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t act_parity[2] = {0, 0};
-      const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
-      for (int64_t pr = 0; pr * 2 < my_tiles; ++pr) {
-        const int nslots = (my_tiles - 2 * pr >= 2) ? 2 : 1;
-        int s0 = 0;
-        for (int bl = 1; bl <= 9; ++bl) {
-          int s1 = s0;
-          while (!c_layout.bwd[s1].last) ++s1;
-          for (int slot = 0; slot < nslots; ++slot) {
-            mbar_wait(bar_act + 8 * slot, act_parity[slot], 700 + bl);
-            act_parity[slot] ^= 1;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-            for (int s = s0; s <= s1; ++s) {
-              const SlabDesc& d = c_layout.bwd[s];
-              mbar_wait(bar_wfull + 8 * stage, phase, 800);
-              tc_fence_after();
-              const uint32_t a_addr = smem_base + kSmemA + slot * kABytes + d.kb * 16384u;
-              const uint32_t b_addr = smem_base + kBwdSmemW + stage * kWStageBytes;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(d_tmem, umma_smem_desc(a_addr + kk * 32, 16, 1024),
-                          umma_smem_desc(b_addr + kk * 32, 16, 1024), idesc, (d.first && kk == 0) ? 0u : 1u);
-              umma_commit(bar_wempty + 8 * stage);
-              if (++stage == kBwdWStages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(bar_acc + 8 * slot);
-          }
-          s0 = s1 + 1;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
 }
 
 // ------------------------------------------------------------------------------- wgrad

@@ -165,10 +165,11 @@ int nb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 int nb200_generate_rays(const float* poses, int P, int H, int W, float f, int64_t ray_begin,
                         int64_t n_rays, float* rays, nb200_stream_t stream) {
   using namespace nb200;
-  if (!poses || !rays || P <= 0 || H <= 0 || W <= 0 || !(f > 0.f) || ray_begin < 0 || n_rays < 0 ||
+  if (P <= 0 || H <= 0 || W <= 0 || !(f > 0.f) || ray_begin < 0 || n_rays < 0 ||
       ray_begin + n_rays > (int64_t)P * H * W)
     return NB200_ERR_ARG;
   if (n_rays == 0) return NB200_OK;
+  if (!poses || !rays) return NB200_ERR_ARG;
   const int64_t blocks = ceil_div64(n_rays, 256);
   const int grid = (int)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
   generate_rays_kernel<<<grid, 256, 0, as_stream(stream)>>>(poses, H, W, f, ray_begin, n_rays, rays);
@@ -179,9 +180,10 @@ int nb200_generate_rays(const float* poses, int P, int H, int W, float f, int64_
 int nb200_stratified_ts(const float* u, uint64_t seed, uint64_t offset, int64_t B, int N, float tn,
                         float tf, float* ts, nb200_stream_t stream) {
   using namespace nb200;
-  if (!ts || B < 0 || N < 1) return NB200_ERR_ARG;
+  if (B < 0 || N < 1) return NB200_ERR_ARG;
   const int64_t total = B * (int64_t)N;
   if (total == 0) return NB200_OK;
+  if (!ts) return NB200_ERR_ARG;
   const int64_t blocks = ceil_div64(ceil_div64(total, 4), 256);
   const int grid = (int)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
   stratified_ts_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total, N, tn, tf, ts);

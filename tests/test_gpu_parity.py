@@ -265,3 +265,32 @@ def test_cpu_tensor_fails_loudly(net):
     from nerf_simple_b200._lib import NerfB200Error
     with pytest.raises(NerfB200Error):
         net(torch.zeros(4, 6))
+
+
+def test_edge_shapes(net, precision):
+    """Empty, single-ray and ragged inputs (the reference's loops silently drop remainders; here
+    every size must work and agree with the full-batch result)."""
+    from nerf_simple_b200 import ops, _lib
+    from nerf_simple_b200.rendering import render_nerf, volume_render
+    g = load_golden("case_render_b1024_n64.npz")
+    rays = torch.from_numpy(g["rays"]).cuda()
+    with torch.no_grad():
+        out = net(torch.zeros((0, 6), device="cuda"))
+        assert out.shape == (0, 4)
+        o5 = render_nerf(rays[:0], net, 16)
+        assert o5[0].shape == (0, 3) and o5[2].shape == (0, 16)
+        torch.manual_seed(11)
+        full = render_nerf(rays, net, 64)[0]
+        torch.manual_seed(11)
+        u = torch.rand(1024, 64)
+        for b0, b1 in ((0, 1), (5, 134), (900, 1024)):                 # 1 ray, 129 rays (tile + 1), tail
+            ts = ops.stratified_ts(b1 - b0, 64, 2, 6, u=u[b0:b1].cuda())
+            o = ops.mlp_apply(net, _lib.IN_RAYS, rays[b0:b1], ts, 64).view(b1 - b0, 64, 4)
+            rgb = ops.composite_apply(o, ts, rays[b0:b1], dirs_mode=1)[0]
+            assert maxabs(rgb, full[b0:b1]) <= 1e-6
+        # N that is neither a multiple of 32 nor of 4
+        torch.manual_seed(3)
+        rgb, disp, alpha, acc, w = render_nerf(rays[:77], net, 37)
+        assert alpha.shape == (77, 37) and bool(torch.isfinite(rgb).all()) and float((acc - 1).abs().max()) <= 1e-4
+    with pytest.raises(ValueError):
+        volume_render(torch.zeros(2, 1, 4, device="cuda"), torch.zeros(2, 1, device="cuda"), torch.zeros(2, 3, device="cuda"))
