@@ -12,6 +12,9 @@
  *     allocates device memory (all workspaces are caller-allocated), nothing synchronises the
  *     device.  Work is enqueued on `stream`.
  *   - all tensors are dense row-major fp32 unless stated; "dev" = device pointer.
+ *   - alignment: [.,4] per-sample tensors (MLP out, its cotangent) 16 bytes, [.,6] ray / point
+ *     tensors 8 bytes (NB200_ERR_ARG otherwise); everything else 4 bytes, with vector fast
+ *     paths taken when 16-byte aligned.  count == 0 succeeds without touching the pointers.
  *   - there is NO CPU fallback: without an sm_100 device the compute calls fail with
  *     NB200_ERR_CUDA / NB200_ERR_ARCH.
  */

@@ -574,6 +574,7 @@ int nb200_composite_forward(const float* outs, const float* ts, const float* dir
   if (B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
   if (B == 0) return NB200_OK;  // empty batch: pointers may be null
   if (!outs || !ts || !dirs || !rgb || !disp || !acc) return NB200_ERR_ARG;
+  if (((uintptr_t)outs & 15) || (dirs_mode == 1 && ((uintptr_t)dirs & 7))) return NB200_ERR_ARG;  // float4 / float2 rows
   cudaStream_t s = as_stream(stream);
   const bool want_aw = alpha != nullptr || weights != nullptr;
   const bool aligned = (((uintptr_t)outs | (uintptr_t)ts | (uintptr_t)alpha | (uintptr_t)weights) & 15) == 0;
@@ -617,6 +618,7 @@ int nb200_composite_backward(const float* outs, const float* ts, const float* di
   if (B < 0 || N < 2 || (dirs_mode != 0 && dirs_mode != 1)) return NB200_ERR_ARG;
   if (B == 0) return NB200_OK;
   if (!outs || !ts || !dirs || !d_rgb || !d_outs) return NB200_ERR_ARG;
+  if ((((uintptr_t)outs | (uintptr_t)d_outs) & 15) || (dirs_mode == 1 && ((uintptr_t)dirs & 7))) return NB200_ERR_ARG;
   cudaStream_t s = as_stream(stream);
   const bool extra = d_disp || d_acc || d_alpha || d_w;
   const bool aligned = (((uintptr_t)outs | (uintptr_t)ts | (uintptr_t)d_outs) & 15) == 0;

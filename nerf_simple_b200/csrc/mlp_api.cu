@@ -62,7 +62,7 @@ int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float*
   int rc = check_common(precision, in_mode, in0, in1, M, N);
   if (rc != NB200_OK) return rc;
   if (M == 0) return NB200_OK;
-  if (!out) return NB200_ERR_ARG;
+  if (!out || ((uintptr_t)out & 15) || ((uintptr_t)in0 & 7)) return NB200_ERR_ARG;  // float4 out rows, float2 input rows
   if (precision == NB200_FP32) {
     if (!params) return NB200_ERR_ARG;
     return nb200::fp32_forward(in_mode, in0, in1, M, N, params, out, saved, scratch, scratch_bytes,
@@ -83,7 +83,7 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
   for (int i = 0; i < 24; ++i)
     if (!grads[i]) return NB200_ERR_ARG;
   if (M == 0) return NB200_OK;  // gradients are accumulated into: nothing to add
-  if (!d_out || !saved) return NB200_ERR_ARG;
+  if (!d_out || !saved || ((uintptr_t)d_out & 15) || ((uintptr_t)in0 & 7)) return NB200_ERR_ARG;
   if (precision == NB200_FP32) {
     if (!params) return NB200_ERR_ARG;
     return nb200::fp32_backward(M, params, d_out, saved, grads, scratch, scratch_bytes,

@@ -76,7 +76,8 @@ __device__ __forceinline__ float tbin(int i, int N, float tn, float tf, float st
 // Each thread produces 4 consecutive samples (one Philox call, one 16 B store when aligned).
 __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restrict__ u, uint64_t seed,
                                                             uint64_t offset, int64_t total, int N,
-                                                            float tn, float tf, float* __restrict__ ts) {
+                                                            float tn, float tf, float* __restrict__ ts,
+                                                            bool vec_ok) {
   const float step = __fdiv_rn(tf - tn, (float)N);
   const float bin = __fsub_rn(tbin(1, N, tn, tf, step), tbin(0, N, tn, tf, step));
   const int64_t nquads = (total + 3) >> 2;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restr
     const int64_t base = q << 2;
     float r[4];
     if (u != nullptr) {
-      if (base + 3 < total) {
+      if (vec_ok && base + 3 < total) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(u + base));
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
       } else {
@@ -107,13 +108,46 @@ __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restr
       // utils/rendering.py:29: bin_diff*unif + t_bins[:-1]; two roundings, never an fma
       o[k] = __fadd_rn(__fmul_rn(bin, r[k]), tbin(i, N, tn, tf, step));
     }
-    if (base + 3 < total) {
+    if (vec_ok && base + 3 < total) {
       *reinterpret_cast<float4*>(ts + base) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (base + k < total) ts[base + k] = o[k];
     }
+  }
+}
+
+// Fast path for N % 4 == 0 (a quad never straddles two rays).  The grid-stride is a multiple of
+// the quads per ray, so a thread always lands on the same four bins: the bin edges are computed
+// once per thread and a quad costs one Philox call + 4 x (shift, I2F, FMUL, FADD).  Same counter
+// convention (offset + quad index) and the same two roundings as the generic kernel above:
+// bin * (m * 2^-24) == m * (bin * 2^-24) exactly, the scale being a power of two.
+template <bool kHasU>
+__global__ void __launch_bounds__(256) stratified_ts_quad_kernel(const float* __restrict__ u, uint64_t seed,
+                                                                 uint64_t offset, int64_t nquads, int N, int64_t stride,
+                                                                 float tn, float tf, float* __restrict__ ts) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= stride) return;
+  const float step = __fdiv_rn(tf - tn, (float)N);
+  const float bin = __fsub_rn(tbin(1, N, tn, tf, step), tbin(0, N, tn, tf, step));
+  const float scale = kHasU ? bin : bin * 5.9604644775390625e-08f;
+  const int i0 = (int)(tid % (N >> 2)) << 2;
+  float tb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tb[k] = tbin(i0 + k, N, tn, tf, step);
+  for (int64_t q = tid; q < nquads; q += stride) {
+    float r[4];
+    if constexpr (kHasU) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(u) + q);
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+      const uint4 x = philox4x32_10(offset + (uint64_t)q, seed);
+      r[0] = (float)(x.x >> 8); r[1] = (float)(x.y >> 8); r[2] = (float)(x.z >> 8); r[3] = (float)(x.w >> 8);
+    }
+    // utils/rendering.py:29: bin_diff*unif + t_bins[:-1]; two roundings, never an fma
+    reinterpret_cast<float4*>(ts)[q] = make_float4(__fadd_rn(__fmul_rn(scale, r[0]), tb[0]), __fadd_rn(__fmul_rn(scale, r[1]), tb[1]),
+                                                   __fadd_rn(__fmul_rn(scale, r[2]), tb[2]), __fadd_rn(__fmul_rn(scale, r[3]), tb[3]));
   }
 }
 
@@ -169,7 +203,7 @@ int nb200_generate_rays(const float* poses, int P, int H, int W, float f, int64_
       ray_begin + n_rays > (int64_t)P * H * W)
     return NB200_ERR_ARG;
   if (n_rays == 0) return NB200_OK;
-  if (!poses || !rays) return NB200_ERR_ARG;
+  if (!poses || !rays || ((uintptr_t)rays & 7)) return NB200_ERR_ARG;  // float2 stores
   const int64_t blocks = ceil_div64(n_rays, 256);
   const int grid = (int)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
   generate_rays_kernel<<<grid, 256, 0, as_stream(stream)>>>(poses, H, W, f, ray_begin, n_rays, rays);
@@ -186,7 +220,17 @@ int nb200_stratified_ts(const float* u, uint64_t seed, uint64_t offset, int64_t 
   if (!ts) return NB200_ERR_ARG;
   const int64_t blocks = ceil_div64(ceil_div64(total, 4), 256);
   const int grid = (int)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
-  stratified_ts_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total, N, tn, tf, ts);
+  const bool aligned = (((uintptr_t)ts | (uintptr_t)u) & 15) == 0;
+  if (N % 4 == 0 && N <= 1024 && aligned) {
+    const int64_t threads = (int64_t)grid * 256;
+    const int64_t stride = threads - threads % (N >> 2);
+    if (u)
+      stratified_ts_quad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts);
+    else
+      stratified_ts_quad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts);
+  } else {
+    stratified_ts_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total, N, tn, tf, ts, aligned);
+  }
   NB_LAUNCH_CHECK("stratified_ts_kernel");
   return NB200_OK;
 }

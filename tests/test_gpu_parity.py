@@ -76,6 +76,16 @@ def test_sampler_bit_exact_and_philox():
     assert bool(((a >= bins[:-1]) & (a <= bins[1:])).all())
     frac = (a - bins[:-1]) / (4 / 64)
     assert abs(float(frac.mean()) - 0.5) < 5e-3 and abs(float(frac.var()) - 1 / 12) < 5e-3
+    # the quad fast path (N % 4 == 0, 16-byte aligned) and the generic kernel draw the same stream:
+    # a misaligned output pointer forces the generic kernel through the C ABI
+    import ctypes
+    from nerf_simple_b200 import _lib
+    lib = _lib.load()
+    for N in (64, 128, 36):
+        fast = ops.stratified_ts(1000, N, 2, 6, device="cuda", seed=9, offset=123)
+        buf = torch.zeros(1000 * N + 1, device="cuda")
+        rc = lib.nb200_stratified_ts(None, 9, 123, 1000, N, 2.0, 6.0, ctypes.c_void_p(buf.data_ptr() + 4), _lib.stream_ptr())
+        assert rc == 0 and torch.equal(buf[1:].view(1000, N), fast)
 
 
 def test_posenc_matches_reference():
