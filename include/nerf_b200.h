@@ -145,6 +145,19 @@ int nb200_sample_pdf_merge(const float* ts, const float* weights, const float* u
 int nb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     int64_t step, float lr, float beta1, float beta2, float eps, nb200_stream_t stream);
 
+/* Device-side ray selection for the device-resident trainer.  Replaces rg.select('train', B) and
+ * train_imgs[ray_ids] of train.py:47-49 (utils/dataload.py:141-153: a CPU randperm over the whole ray
+ * table per step).  B indices uniform in [0, n_table) WITH replacement from Philox4x32-10 keyed by
+ * (seed, offset + i); gathers rays_table [n_table,6] -> rays [B,6] and, when gt_table != NULL,
+ * gt_table [n_table,3] -> gt [B,3].  ids (dev int64 [B]) may be NULL. */
+int nb200_select_rays(const float* rays_table, const float* gt_table, int64_t n_table, uint64_t seed,
+                      uint64_t offset, int64_t B, float* rays, float* gt, int64_t* ids, nb200_stream_t stream);
+
+/* MSELoss(rgb_, gt_) and its gradient.  Replaces train.py:42,52 + the first autograd node of :54:
+ * loss = mean over B*3 of (rgb-gt)^2 (written to *loss when non-NULL), d_rgb = 2 (rgb-gt) / (3B). */
+int nb200_mse_loss_grad(const float* rgb, const float* gt, int64_t B, float* d_rgb, float* loss,
+                        nb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -378,7 +378,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   // 2. weight gradients: (delta tensor, input tensor) pairs
   WgradParams wp;
   memset(&wp, 0, sizeof(wp));
-  wp.T = T;
+  wp.T = T; wp.M = M; wp.d_out = d_out;
   int n = 0;
   auto item = [&](int dt, int st, int layer, int ldw, int col0, int ncols, int nrows, bool bias) {
     WItem& w = wp.items[n++];
@@ -392,10 +392,22 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     w.dW = G[2 * layer]; w.db = bias ? G[2 * layer + 1] : nullptr;
     w.ldw = ldw; w.col0 = col0; w.ncols = ncols; w.nrows = nrows;
     w.cost = (w.a_chunks + w.b_chunks) * 16;
+    w.head = 0; w.x_ptr = nullptr; w.x_tile_bytes = 0; w.x_chunks = 0; w.hW = nullptr; w.hb = nullptr;
+  };
+  // the sigma / colour head gradients ride on the item that stages their input (h7 / an extra c1 slab)
+  auto head = [&](int which, int st, int layer) {
+    WItem& w = wp.items[n - 1];
+    w.head = which; w.hW = G[2 * layer]; w.hb = G[2 * layer + 1];
+    if (which == 2) {
+      w.x_ptr = sv + saved_tensor_off(st, T); w.x_tile_bytes = (uint32_t)saved_tile_bytes(st); w.x_chunks = 2;
+      w.cost += w.x_chunks * 16;
+    }
   };
   item(0, 8, L_C0, kHidden + kPosD, 0, kHidden, kHidden / 2, true);        // color_fc.0 <- g
   item(0, 11, L_C0, kHidden + kPosD, kHidden, kPosD, kHidden / 2, false);  // color_fc.0 <- posd
+  head(2, 9, L_C1);                                                         // color_fc.2 <- c1 (CUDA cores)
   item(1, 7, L_2, kHidden, 0, kHidden, kHidden, true);                      // layers_2   <- h7
+  head(1, 7, L_SIGMA);                                                      // sigma_fc   <- h7 (CUDA cores)
   item(2, 6, L1_1, kHidden, 0, kHidden, kHidden, true);                     // layers_1.2 <- h6
   item(3, 5, L1_0, kHidden, 0, kHidden, kHidden, true);                     // layers_1.0 <- h5
   item(4, 4, L_SKIP, kHidden + kPosX, 0, kHidden, kHidden, true);           // skip       <- h4
@@ -405,17 +417,12 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   item(7, 1, L0_2, kHidden, 0, kHidden, kHidden, true);
   item(8, 0, L0_1, kHidden, 0, kHidden, kHidden, true);
   item(9, 10, L0_0, kPosX, 0, kPosX, kHidden, true);                        // layers_0.0 <- posx
+  // measured: a 32-row stage costs a fixed latency share on top of its bytes (the 6-stage ring is
+  // latency-bound for small stages); 96 'KB-equivalents' per tile balances the CTAs best (sweep 0..384)
+  for (int i = 0; i < n; ++i) wp.items[i].cost += 96;
   wp.num_items = n;
   mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");
-  // 3. sigma / colour heads
-  {
-    const int64_t want = ceil_div64(T * 8, 8 * 4);  // ~4 (tile, row-group) items per warp
-    const int64_t cap = (int64_t)sm_count() * 4;
-    mlp_head_grads_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, s>>>(
-        sv, d_out, M, T, G[2 * L_SIGMA], G[2 * L_SIGMA + 1], G[2 * L_C1], G[2 * L_C1 + 1]);
-    NB_LAUNCH_CHECK("mlp_head_grads_kernel");
-  }
   return NB200_OK;
 }
 

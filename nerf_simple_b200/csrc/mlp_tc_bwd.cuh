@@ -8,7 +8,8 @@
 //       are the saved tile images read as MN-major UMMA operands (K = samples); accumulators live in
 //       TMEM across the CTA's whole tile range, bias gradients are column sums taken from the staged
 //       delta tiles by otherwise idle warps, one atomic flush per (CTA, layer) segment.
-//   mlp_head_grads_kernel: the 256->1 sigma head and 128->3 colour head on CUDA cores.
+//       The 256->1 sigma head and the 128->3 colour head gradients ride along on those warps (CUDA
+//       cores) while h7 / c1 are staged, so the heads need no pass of their own.
 
 // ------------------------------------------------------------------ delta scratch layout
 // tensor 0 = delta_c1 (128 cols, 32 KB/tile); tensors 1..9 = delta_g, delta_h7, ..., delta_h0 (64 KB/tile)
@@ -37,6 +38,12 @@ __device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t v, uint32_t h) {
 }
 
 // ------------------------------------------------------------------------------- wgrad
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
 struct WItem {
   const uint8_t* a_ptr;   // delta tensor (tile images): A operand, M = output features
   const uint8_t* b_ptr;   // layer input tensor (tile images): B operand, N = input features
@@ -48,16 +55,29 @@ struct WItem {
   int b_chunks;           // 64-column chunks of the input staged: 1 or 4
   int n_mma;              // UMMA N: 256 or 64
   int cost;               // relative cost per tile (KB staged), for the work split
+  // head gradients ride along on the CUDA-core warps (no MMA):
+  //   head 1: dW_sigma[256] += d_sigma^T . (B operand = h7), db_sigma += sum d_sigma
+  //   head 2: dW_c1[3,128] += d_rgb^T . c1, db_c1 += sum d_rgb; c1 (x_chunks = 2) is staged behind
+  //           the B chunks only for this purpose
+  int head;
+  const uint8_t* x_ptr;
+  uint32_t x_tile_bytes;
+  int x_chunks;
+  float* hW;              // gradient of the head weight
+  float* hb;              // gradient of the head bias
 };
 constexpr int kMaxWItems = 12;
 struct WgradParams {
   WItem items[kMaxWItems];
   int num_items;
   int64_t T;
+  int64_t M;
+  const float* d_out;     // [M,4] cotangent of (r,g,b,sigma): the head "deltas"
 };
 
-constexpr int kWgStages = 6;
-constexpr uint32_t kWgStageBytes = 32768;  // 32 sample rows: A chunks 4 x 4 KB | B chunks 4 x 4 KB
+constexpr int kWgStages = 6;  // (an extra L2 prefetch ahead of the ring was measured: 548 -> 742 us, so there is none)
+constexpr uint32_t kWgStageData = 32768;   // 32 sample rows: A chunks 4 x 4 KB | B chunks 4 x 4 KB
+constexpr uint32_t kWgStageBytes = kWgStageData + 1024;  // + d_out rows of the stage (512 B) for the head items
 constexpr uint32_t kWgSmemBar = kWgStages * kWgStageBytes;  // 196608
 constexpr uint32_t kWgSmemLaunch = kWgSmemBar + 256 + 1024;
 constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 bias sums + flush
@@ -116,13 +136,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
         for (int64_t tile = tb; tile < te; ++tile) {
           for (int sub = 0; sub < 4; ++sub) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 900);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(w.a_chunks + w.b_chunks) * 4096u);
+            // head items also stage the 32 d_out rows (the global-load latency under a saturated HBM is
+            // several stage periods, so they have to travel with the stage)
+            const int64_t m0 = tile * kTileM + sub * 32;
+            const uint32_t g_bytes = !w.head || m0 >= p.M ? 0u : (uint32_t)((p.M - m0 < 32 ? p.M - m0 : 32) * 16);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(w.a_chunks + w.b_chunks + w.x_chunks) * 4096u + g_bytes);
             const uint32_t dst = smem_base + stage * kWgStageBytes;
+            if (g_bytes) tma_bulk_g2s(dst + kWgStageData, p.d_out + m0 * 4, g_bytes, bar_full + 8 * stage);
             for (int c = 0; c < w.a_chunks; ++c)
               tma_bulk_g2s(dst + c * 4096, w.a_ptr + (size_t)tile * w.a_tile_bytes + c * 16384 + sub * 4096, 4096,
                            bar_full + 8 * stage);
             for (int c = 0; c < w.b_chunks; ++c)
               tma_bulk_g2s(dst + 16384 + c * 4096, w.b_ptr + (size_t)tile * w.b_tile_bytes + c * 16384 + sub * 4096,
+                           4096, bar_full + 8 * stage);
+            for (int c = 0; c < w.x_chunks; ++c)
+              tma_bulk_g2s(dst + 16384 + (w.b_chunks + c) * 4096, w.x_ptr + (size_t)tile * w.x_tile_bytes + c * 16384 + sub * 4096,
                            4096, bar_full + 8 * stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
@@ -173,9 +201,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
       if (te <= tb) continue;
       float b0 = 0.f, b1 = 0.f;
       const bool do_bias = (w.db != nullptr) && (cw < w.a_chunks);
+      float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // head 1: [0..1]; head 2: (r,g,b) x 2 columns
+      float4 hbias = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int head = w.head;
       for (int64_t tile = tb; tile < te; ++tile) {
         for (int sub = 0; sub < 4; ++sub) {
           mbar_wait(bar_full + 8 * stage, phase, 1200);
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);      // d_out row `lane` of this 32-row stage
+          const uint32_t g_smem = smem_base + stage * kWgStageBytes + kWgStageData;
+          if (head) {
+            if (tile * kTileM + sub * 32 + lane < p.M)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                           : "r"(g_smem + lane * 16));
+            else  // tail of the last tile: rows >= M were not copied; every warp zeroes them for its own reads
+              asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(g_smem + lane * 16), "f"(0.f));
+            __syncwarp();
+            hbias.x += g.x; hbias.y += g.y; hbias.z += g.z; hbias.w += g.w;
+          }
           if (do_bias) {
             const uint32_t base = smem_base + stage * kWgStageBytes + cw * 4096 + (lane & 3) * 4;
 #pragma unroll 8
@@ -186,9 +228,70 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
               b1 += __uint_as_float(v & 0xFFFF0000u);
             }
           }
+          if (head == 1) {
+            // warp cw: columns [64 cw, 64 cw + 64) of h7; the d_sigma of a row is a broadcast shared load
+            const uint32_t base = smem_base + stage * kWgStageBytes + 16384 + cw * 4096 + (lane & 3) * 4;
+#pragma unroll
+            for (int rb = 0; rb < 32; rb += 8) {   // 8 rows per batch: all loads first, then the FMAs
+              uint32_t v[8];
+              float gs[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(base + (rb + i) * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)i) << 4)));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gs[i]) : "r"(g_smem + (rb + i) * 16 + 12));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                hacc[2 * (i & 1)] = fmaf(gs[i], __uint_as_float(v[i] << 16), hacc[2 * (i & 1)]);
+                hacc[2 * (i & 1) + 1] = fmaf(gs[i], __uint_as_float(v[i] & 0xFFFF0000u), hacc[2 * (i & 1) + 1]);
+              }
+            }
+          } else if (head == 2) {
+            // warp cw: columns [64 (cw&1), +64) of c1, rows [16 (cw>>1), +16) of the stage
+            const uint32_t base = smem_base + stage * kWgStageBytes + 16384 + (w.b_chunks + (cw & 1)) * 4096 + (lane & 3) * 4;
+#pragma unroll
+            for (int rb = 0; rb < 16; rb += 8) {
+              const int r0 = (cw >> 1) * 16 + rb;
+              uint32_t v[8];
+              float4 gq[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(base + (r0 + i) * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)i) << 4)));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(gq[i].x), "=f"(gq[i].y), "=f"(gq[i].z), "=f"(gq[i].w)
+                             : "r"(g_smem + (r0 + i) * 16));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float c0 = __uint_as_float(v[i] << 16), c1 = __uint_as_float(v[i] & 0xFFFF0000u);
+                hacc[0] = fmaf(gq[i].x, c0, hacc[0]); hacc[1] = fmaf(gq[i].x, c1, hacc[1]);
+                hacc[2] = fmaf(gq[i].y, c0, hacc[2]); hacc[3] = fmaf(gq[i].y, c1, hacc[3]);
+                hacc[4] = fmaf(gq[i].z, c0, hacc[4]); hacc[5] = fmaf(gq[i].z, c1, hacc[5]);
+              }
+            }
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (head == 1) {
+        const int n = cw * 64 + 2 * lane;
+        atomicAdd(w.hW + n, hacc[0] + hacc[2]);          // even + odd row partial sums
+        atomicAdd(w.hW + n + 1, hacc[1] + hacc[3]);
+        if (cw == 0) {
+          const float tot = warp_sum_f(hbias.w);
+          if (lane == 0) atomicAdd(w.hb, tot);
+        }
+      } else if (head == 2) {
+        const int n = (cw & 1) * 64 + 2 * lane;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          atomicAdd(w.hW + k * 128 + n, hacc[2 * k]);
+          atomicAdd(w.hW + k * 128 + n + 1, hacc[2 * k + 1]);
+        }
+        if (cw == 2) {
+          const float tr = warp_sum_f(hbias.x), tg = warp_sum_f(hbias.y), tbl = warp_sum_f(hbias.z);
+          if (lane == 0) { atomicAdd(w.hb, tr); atomicAdd(w.hb + 1, tg); atomicAdd(w.hb + 2, tbl); }
         }
       }
       if (do_bias) {
@@ -236,88 +339,3 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
   }
 }
 
-// -------------------------------------------------------------------- head gradients
-// dW_sigma[256] = sum_m d_sigma[m] h7[m,:],  dW_c1[3,128] = sum_m d_rgb[m,:]^T c1[m,:], and both
-// biases (CUDA cores; 0.78 KB/sample of saved bf16 tiles are read once, fully coalesced).
-// A warp takes 16 rows of a tile per step; lane l owns the 16-byte chunk (K-block l>>3, chunk l&7)
-// of every row: 8 columns of h7 for all lanes, 8 columns of c1 for lanes 0..15.
-__device__ __forceinline__ void unpack_bf16x8(const uint4& v, float (&f)[8]) {
-  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xFFFF0000u);
-  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xFFFF0000u);
-  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xFFFF0000u);
-  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xFFFF0000u);
-}
-
-__global__ void __launch_bounds__(256) mlp_head_grads_kernel(const uint8_t* __restrict__ saved, const float* __restrict__ d_out,
-                                                             int64_t M, int64_t T, float* __restrict__ gWsig,
-                                                             float* __restrict__ gbsig, float* __restrict__ gWc1,
-                                                             float* __restrict__ gbc1) {
-  __shared__ float red[8][32 * 33];  // per-warp partials: [lane][8 sigma + 24 colour (+1 pad)]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t kb = lane >> 3, j = lane & 7;
-  float as[8], ac[24], bs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) as[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 24; ++i) ac[i] = 0.f;
-  const int64_t items = T * 8, stride = (int64_t)gridDim.x * 8;
-  for (int64_t it = (int64_t)blockIdx.x * 8 + warp; it < items; it += stride) {
-    const int64_t tile = it >> 3;
-    const int r0 = (int)(it & 7) * 16;
-    const uint8_t* h7 = saved + saved_tensor_off(7, T) + (size_t)tile * 65536 + kb * 16384u;
-    const uint8_t* c1 = saved + saved_tensor_off(9, T) + (size_t)tile * 32768 + (kb & 1u) * 16384u;
-#pragma unroll 1
-    for (int rb = 0; rb < 16; rb += 8) {
-      // 8 rows at a time, every load issued before the math (24 independent 16-byte requests per lane)
-      float4 g[8];
-      uint4 hv[8], cv[8];
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = r0 + rb + rr;
-        const int64_t m = tile * kTileM + r;
-        const uint32_t off = (uint32_t)r * 128u + ((j ^ ((uint32_t)r & 7u)) << 4);
-        g[rr] = (m < M) ? __ldg(reinterpret_cast<const float4*>(d_out) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-        hv[rr] = __ldg(reinterpret_cast<const uint4*>(h7 + off));
-        cv[rr] = (lane < 16) ? __ldg(reinterpret_cast<const uint4*>(c1 + off)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        float f[8];
-        unpack_bf16x8(hv[rr], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) as[e] = fmaf(g[rr].w, f[e], as[e]);
-        unpack_bf16x8(cv[rr], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          ac[e] = fmaf(g[rr].x, f[e], ac[e]);
-          ac[8 + e] = fmaf(g[rr].y, f[e], ac[8 + e]);
-          ac[16 + e] = fmaf(g[rr].z, f[e], ac[16 + e]);
-        }
-        bs[0] += g[rr].x; bs[1] += g[rr].y; bs[2] += g[rr].z; bs[3] += g[rr].w;
-      }
-    }
-  }
-  float* mine = &red[warp][lane * 33];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) mine[i] = as[i];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) mine[8 + i] = ac[i];
-  mine[32] = 0.f;
-  __syncthreads();
-  // thread t sums slot t over the 8 warps: slot = lane_src*33 + k  (1056 slots, 256 threads)
-  for (int slot = threadIdx.x; slot < 32 * 33; slot += 256) {
-    const int ls = slot / 33, k = slot - ls * 33;
-    if (k == 32) continue;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w][slot];
-    const int col = (ls >> 3) * 64 + (ls & 7) * 8;  // first column of lane ls's chunk
-    if (k < 8) atomicAdd(gWsig + col + k, v);
-    else if (ls < 16) atomicAdd(gWc1 + ((k - 8) >> 3) * 128 + col + ((k - 8) & 7), v);
-  }
-  // bias sums: lane 0 of every warp
-  if (lane == 0) {
-    atomicAdd(gbc1, bs[0]); atomicAdd(gbc1 + 1, bs[1]); atomicAdd(gbc1 + 2, bs[2]);
-    atomicAdd(gbsig, bs[3]);
-  }
-}

@@ -179,6 +179,58 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   }
 }
 
+// ---------------------------------------------------------------------- train-step helpers
+// Ray selection on the device: rg.select('train', B) + train_imgs[ray_ids] (train.py:47-49,
+// utils/dataload.py:141-153).  The reference draws a CPU randperm over the whole table (328 ms per
+// step); here B indices are drawn uniformly WITH replacement from Philox (seed, offset + i) and
+// the 24-byte ray row and 12-byte colour row are gathered in the same kernel.
+__global__ void __launch_bounds__(256) select_rays_kernel(const float* __restrict__ rays_table,
+                                                          const float* __restrict__ gt_table, int64_t n_table,
+                                                          uint64_t seed, uint64_t offset, int64_t B,
+                                                          float* __restrict__ rays, float* __restrict__ gt,
+                                                          int64_t* __restrict__ ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const uint4 x = philox4x32_10(offset + (uint64_t)i, seed);
+  // 64 random bits -> [0, n_table): high word of the 64x64 product (bias < n_table * 2^-64)
+  const uint64_t r64 = ((uint64_t)x.y << 32) | x.x;
+  const int64_t id = (int64_t)__umul64hi(r64, (uint64_t)n_table);
+  const float2* src = reinterpret_cast<const float2*>(rays_table + id * 6);
+  float2* dst = reinterpret_cast<float2*>(rays + i * 6);
+  const float2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+  dst[0] = a; dst[1] = b; dst[2] = c;
+  if (gt_table != nullptr) {
+    gt[i * 3] = __ldg(gt_table + id * 3);
+    gt[i * 3 + 1] = __ldg(gt_table + id * 3 + 1);
+    gt[i * 3 + 2] = __ldg(gt_table + id * 3 + 2);
+  }
+  if (ids != nullptr) ids[i] = id;
+}
+
+// MSELoss(rgb, gt) over B*3 values and its gradient (train.py:42,52): loss = mean((rgb-gt)^2),
+// d_rgb = 2 (rgb - gt) / (3B).  One block, fixed summation order (deterministic loss).
+__global__ void __launch_bounds__(1024) mse_loss_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ gt,
+                                                             int64_t n, float* __restrict__ d_rgb, float* __restrict__ loss) {
+  __shared__ float part[32];
+  const float scale = 2.0f / (float)n;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = rgb[i] - gt[i];
+    d_rgb[i] = d * scale;
+    acc = fmaf(d, d, acc);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0 && loss != nullptr) *loss = v / (float)n;
+  }
+}
+
 }  // namespace nb200
 
 extern "C" {
@@ -232,6 +284,27 @@ int nb200_stratified_ts(const float* u, uint64_t seed, uint64_t offset, int64_t 
     stratified_ts_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total, N, tn, tf, ts, aligned);
   }
   NB_LAUNCH_CHECK("stratified_ts_kernel");
+  return NB200_OK;
+}
+
+int nb200_select_rays(const float* rays_table, const float* gt_table, int64_t n_table, uint64_t seed,
+                      uint64_t offset, int64_t B, float* rays, float* gt, int64_t* ids, nb200_stream_t stream) {
+  using namespace nb200;
+  if (B < 0 || n_table <= 0) return NB200_ERR_ARG;
+  if (B == 0) return NB200_OK;
+  if (!rays_table || !rays || (gt_table && !gt)) return NB200_ERR_ARG;
+  if ((((uintptr_t)rays_table | (uintptr_t)rays) & 7) != 0) return NB200_ERR_ARG;
+  select_rays_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, as_stream(stream)>>>(rays_table, gt_table, n_table, seed, offset,
+                                                                                B, rays, gt, ids);
+  NB_LAUNCH_CHECK("select_rays_kernel");
+  return NB200_OK;
+}
+
+int nb200_mse_loss_grad(const float* rgb, const float* gt, int64_t B, float* d_rgb, float* loss, nb200_stream_t stream) {
+  using namespace nb200;
+  if (B <= 0 || !rgb || !gt || !d_rgb) return NB200_ERR_ARG;
+  mse_loss_grad_kernel<<<1, 1024, 0, as_stream(stream)>>>(rgb, gt, B * 3, d_rgb, loss);
+  NB_LAUNCH_CHECK("mse_loss_grad_kernel");
   return NB200_OK;
 }
 

@@ -79,6 +79,11 @@ class Trainer:
         self._rgb = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
         self._disp = torch.empty((self.B,), dtype=torch.float32, device=self.device)
         self._acc = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        self._rays = torch.empty((self.B, 6), dtype=torch.float32, device=self.device)
+        self._gt = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
+        self._drgb = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
+        self._loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._sel_offset = 0
         self._offset = 0
         self.launches = 0
         self.last_loss = None
@@ -88,9 +93,11 @@ class Trainer:
         dev, B, N, M = self.device, self.B, self.N, self.B * self.N
         st = _lib.stream_ptr(dev)
         # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
-        ids = torch.randint(0, self.rays_table.shape[0], (B,), device=dev, generator=self.gen)
-        rays = self.rays_table.index_select(0, ids)
-        gt = self.gt_table.index_select(0, ids)
+        rays, gt = self._rays, self._gt
+        _lib.check(lib.nb200_select_rays(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
+                                         self.seed ^ 0x5E1EC7, self._sel_offset, B, _lib.ptr(rays), _lib.ptr(gt), None, st),
+                   "nb200_select_rays")
+        self._sel_offset += B
         ts = ops.stratified_ts(B, N, self.tn, self.tf, device=dev, seed=self.seed, offset=self._offset)
         self._offset += (M + 3) // 4
         packed = self.net._packed.get(self.params, self.precision)
@@ -101,9 +108,10 @@ class Trainer:
         _lib.check(lib.nb200_composite_forward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, B, N,
                                                _lib.ptr(self._rgb), _lib.ptr(self._disp), _lib.ptr(self._acc),
                                                None, None, st), "nb200_composite_forward")
-        diff = self._rgb - gt                                  # MSELoss over B*3 (train.py:42,52)
-        loss = (diff * diff).mean()
-        d_rgb = diff * (2.0 / (3 * B))
+        # MSELoss over B*3 and its gradient (train.py:42,52)
+        d_rgb, loss = self._drgb, self._loss
+        _lib.check(lib.nb200_mse_loss_grad(_lib.ptr(self._rgb), _lib.ptr(gt), B, _lib.ptr(d_rgb), _lib.ptr(loss), st),
+                   "nb200_mse_loss_grad")
         _lib.check(lib.nb200_composite_backward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, _lib.ptr(d_rgb),
                                                 None, None, None, None, B, N, _lib.ptr(self._dout), st),
                    "nb200_composite_backward")
@@ -119,9 +127,9 @@ class Trainer:
                                        self.betas[1], self.eps, st), "nb200_adam_step")
         self._bump_versions()
         self.lr *= self.lr_decay
-        self.launches += 11 if self.precision == _lib.BF16 else 62   # ts, pack x2, fwd, comp fwd/bwd, dgrad, wgrad, heads, adam
+        self.launches += 12 if self.precision == _lib.BF16 else 64   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), adam (+ memset)
         self.last_loss = loss
-        return float(loss) if sync_loss else loss
+        return float(loss) if sync_loss else loss.clone()
 
     def _bump_versions(self):
         # the optimizer updated the flat buffer, not the 24 views: invalidate the packed-weight cache

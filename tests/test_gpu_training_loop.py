@@ -113,3 +113,42 @@ def test_flat_adam_matches_torch_adam():
                                  _lib.stream_ptr())
         assert rc == 0
     assert float((p - ref.detach()).abs().max()) <= 1e-6
+
+
+def test_select_rays_and_mse_kernels():
+    """Device ray selection (train.py:47-49) and MSELoss + gradient (train.py:42,52-54) through the C ABI."""
+    from nerf_simple_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    n, B = 100003, 8192
+    table = torch.randn(n, 6, device="cuda")
+    gt_table = torch.rand(n, 3, device="cuda")
+    rays, gt = torch.empty(B, 6, device="cuda"), torch.empty(B, 3, device="cuda")
+    ids = torch.empty(B, dtype=torch.int64, device="cuda")
+
+    def select(seed, off, ids_t=ids):
+        rc = lib.nb200_select_rays(_lib.ptr(table), _lib.ptr(gt_table), n, seed, off, B, _lib.ptr(rays), _lib.ptr(gt),
+                                   _lib.ptr(ids_t), _lib.stream_ptr())
+        assert rc == 0
+        return ids_t.clone()
+
+    a = select(3, 0)
+    assert int(a.min()) >= 0 and int(a.max()) < n
+    assert torch.equal(rays, table[a]) and torch.equal(gt, gt_table[a])          # gather == table[ids]
+    assert torch.equal(select(3, 0), a) and not torch.equal(select(4, 0), a)       # keyed by (seed, offset)
+    assert torch.equal(select(3, 100)[:-100], a[100:])                             # offset = position in the stream
+    # uniform over the table: mean / variance of ids/n, and every decile populated evenly
+    u = a.double() / n
+    assert abs(float(u.mean()) - 0.5) < 0.02 and abs(float(u.var()) - 1 / 12) < 0.01
+    hist = torch.histc(u.float(), bins=10, min=0, max=1)
+    assert float(hist.min()) > 0.8 * B / 10 and float(hist.max()) < 1.2 * B / 10
+    assert lib.nb200_select_rays(_lib.ptr(table), None, n, 1, 0, 0, None, None, None, _lib.stream_ptr()) == 0    # empty batch
+    # MSE: loss and gradient against torch autograd
+    rgb = torch.rand(B, 3, device="cuda", requires_grad=True)
+    loss_ref = torch.nn.MSELoss()(rgb, gt)
+    loss_ref.backward()
+    d_rgb, loss = torch.empty(B, 3, device="cuda"), torch.zeros((), device="cuda")
+    rc = lib.nb200_mse_loss_grad(_lib.ptr(rgb.detach()), _lib.ptr(gt), B, _lib.ptr(d_rgb), _lib.ptr(loss), _lib.stream_ptr())
+    assert rc == 0
+    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * max(1.0, float(loss_ref))
+    assert float((d_rgb - rgb.grad).abs().max()) <= 1e-9 + 1e-6 * float(rgb.grad.abs().max())
