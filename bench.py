@@ -169,7 +169,8 @@ def b200_arm(args, rank, local_rank, world):
     poses = torch.stack(poses_to_render(4, -30, 30)).to(dev)
     n_poses = poses.shape[0]
     net_fine = Nerf().to(dev) if args.fine > 0 else None     # --fine 128: hierarchical extension (config 4)
-    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=args.fine)
+    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=args.fine,
+                         fused=(args.render_path == "fused"))
     n_rays = H * W
     gather_buf = [torch.empty((n_rays, 4), device=dev) for _ in range(world)] if world > 1 else None
 
@@ -260,18 +261,22 @@ def b200_arm(args, rank, local_rank, world):
                                    f"(poses_to_render(4,-30,30)), one frame per GPU per step",
                        "H": H, "W": W, "N": N, "N_fine": args.fine, "rays_per_step_per_gpu": n_rays, "weights": "torch.manual_seed(0); Nerf()",
                        "sampler": "device Philox seed 1", "parallelism": f"frames sharded over {world} rank(s) + all_gather of pixels",
-                       "l2": "inputs larger than L2: 655 MB of per-sample (r,g,b,sigma) + 164 MB of ts per frame"},
+                       "render_path": ("one kernel per frame (camera -> sampler -> MLP -> compositing in chain_kernel<FwdEpi<render>>)"
+                                       if rend.fused else "4 kernels per frame: raygen, Philox sampler, fused posenc+MLP, compositing"),
+                       "l2": ("fused path: nothing but the 3.4 MB weight image (L2-resident by design) is re-read between steps; 10 MB of pixels written per frame"
+                              if rend.fused else f"inputs larger than L2: {n_rays * N * 16 / 1e6:.0f} MB of per-sample (r,g,b,sigma) + {n_rays * N * 4 / 1e6:.0f} MB of ts per frame")},
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": n_rays * 16, "api": "FrameRenderer.render_frame_host(pose_pinned) -> pinned frame"},
             "e2e_render_image_api": {"value": api_val, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24,
                                      "d2h_bytes_per_step": n_rays * 16,
                                      "api": "render_image(net, rg, batch_size=16000): CPU ray table, 40 chunks, CPU frame"},
             "gpu_launches": gpu_launches,
-            "roofline": {"kernel": "chain_kernel<FwdEpi<false>> (fused posenc+MLP, tcgen05 cta_group::2)", "bound": "tensor", "achieved": achieved, "peak": pk["sustained"],
+            "roofline": {"kernel": ("chain_kernel<FwdEpi<render>> (camera rays + sampler + posenc + MLP + compositing, tcgen05 cta_group::2)" if rend.fused
+                                     else "chain_kernel<FwdEpi<false>> (fused posenc+MLP, tcgen05 cta_group::2)"), "bound": "tensor", "achieved": achieved, "peak": pk["sustained"],
                          "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "peak_burst": pk["burst"],
                          "frac_burst": achieved / pk["burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                          "kernel_ms": mlp_ms, "flop_per_launch": FLOP_FWD * M,
-                         "traffic": 792493568 if (H, W, N) == (800, 800, 64) else None,
+                         "traffic": 792493568 if (H, W, N) == (800, 800, 64) and not rend.fused else None,
                          "traffic_source": "dram__bytes_read+write.sum of one launch, profiles/r1_fwd_chain_v2_ncu_raw.csv "
                                            "(algorithmic: 655 MB out + 164 MB ts + 15 MB rays)"},
             "clocks": clocks, "outputs_finite": finite,
@@ -383,6 +388,8 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fine", type=int, default=0, help="extension: fine samples per ray (64 coarse + N fine)")
+    ap.add_argument("--render-path", default="separate", choices=["separate", "fused"],
+                    help="separate: raygen, sampler, fused posenc+MLP, compositing kernels; fused: one kernel per frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

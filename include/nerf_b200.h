@@ -130,6 +130,23 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
                        const void* saved, float* const* grads, void* scratch,
                        size_t scratch_bytes, nb200_stream_t stream);
 
+/* Fused render: sampler -> posenc + MLP -> compositing in ONE kernel for the
+ * no-grad render loops (utils/rendering.py:88-153 calling render_nerf, :13-45).  Per-sample
+ * (r,g,b,sigma) and the sample depths stay on chip; only rgb [B,3], disp [B], acc [B] are written.
+ * Results equal nb200_stratified_ts + nb200_mlp_forward(NB200_IN_RAYS) + nb200_composite_forward
+ * (dirs_mode 1) on the same inputs.  NB200_BF16 only, N in {32, 64, 128} (whole rays per 128-sample
+ * tile); otherwise NB200_ERR_UNSUPPORTED and the caller uses the three separate calls.
+ *   ts != NULL: sample depths dev [B,N] supplied (reference-RNG mode).
+ *   ts == NULL: Philox depths, the stream nb200_stratified_ts(NULL, seed, offset, ...) would write. */
+int nb200_render_rays(int precision, const float* rays, const float* ts, uint64_t seed, uint64_t offset,
+                      int64_t B, int N, float tn, float tf, const void* packed, float* rgb, float* disp,
+                      float* acc, nb200_stream_t stream);
+/* Same, with the rays generated in the kernel from the camera (what nb200_generate_rays would write
+ * for rays [ray_begin, ray_begin + n_rays) of the P*H*W table): a whole frame is one launch. */
+int nb200_render_camera(int precision, const float* poses, int P, int H, int W, float f, int64_t ray_begin,
+                        int64_t n_rays, uint64_t seed, uint64_t offset, int N, float tn, float tf,
+                        const void* packed, float* rgb, float* disp, float* acc, nb200_stream_t stream);
+
 /* EXTENSION (no reference counterpart: hierarchical sampling is "not implemented yet" in the
  * reference, configs/lego.yaml:7).  Inverse-CDF importance sampler of the NeRF paper (sec. 5.2):
  * pdf = weights[:,1:-1] + 1e-5 over the mid-point bins of ts [B,Nc], Nf samples per ray drawn with

@@ -38,6 +38,8 @@ SYMBOLS = {
     "nb200_mlp_forward": (_i, [_i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "nb200_mlp_backward": (_i, [_i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _p]),
+    "nb200_render_rays": (_i, [_i, _p, _p, _u64, _u64, _i64, _i, _f, _f, _p, _p, _p, _p, _p]),
+    "nb200_render_camera": (_i, [_i, _p, _i, _i, _i, _f, _i64, _i64, _u64, _u64, _i, _f, _f, _p, _p, _p, _p, _p]),
     "nb200_select_rays": (_i, [_p, _p, _i64, _u64, _u64, _i64, _p, _p, _p, _p]),
     "nb200_mse_loss_grad": (_i, [_p, _p, _i64, _p, _p, _p]),
     "nb200_sample_pdf_merge": (_i, [_p, _p, _p, _i, _u64, _u64, _i64, _i, _i, _p, _p]),

@@ -12,6 +12,7 @@
 // Algorithmic bytes: fwd 20 B/sample read + 20 B/ray written (+8 B/sample when
 // alpha/weights are requested); bwd 36 B/sample (20 read + 16 written) + 12..20 B/ray.
 #include "common.cuh"
+#include "stream_common.cuh"
 
 namespace nb200 {
 
@@ -46,16 +47,6 @@ constexpr int kWarpsPerBlock = 8;
 // transcendental functions use the MUFU units (ex2/lg2.approx, <= 2^-21 relative error; the
 // compositing outputs stay within 5e-6 of the reference's libm-based fp32 math).
 __device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
-__device__ __forceinline__ float exp2f_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2f_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float softplus_ref(float x) {
   // F.softplus(beta=1, threshold=20): utils/rendering.py:67
   // log1p(e) needs RELATIVE accuracy for tiny e: the last sample multiplies it by delta = 1e10 (:61),
@@ -131,12 +122,6 @@ __device__ __forceinline__ float excl_cumprod(float fac, float& carry, int lane)
   return T;
 }
 
-__device__ __forceinline__ float disparity(float depth, float acc) {
-  const float q = __fdividef(depth, acc);                      // :82 depth / sum(weights)
-  const float m = (q != q) ? q : fmaxf(1e-10f, q);             // torch.max propagates NaN
-  return __frcp_rn(m);                                         // :83
-}
-
 // Sum 16 per-lane values across the warp with 16 shuffles (a butterfly that halves the number of
 // live values at every step); afterwards lane L holds the total of value L >> 1.
 __device__ __forceinline__ float warp_multi_sum16(float (&v)[16], int lane) {
@@ -151,20 +136,6 @@ __device__ __forceinline__ float warp_multi_sum16(float (&v)[16], int lane) {
     }
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-// exp(-softplus(sigma) * delta) with the two natural-log constants cancelled:
-//   (1 + e^sigma)^(-delta) = ex2(-delta * lg2(1 + ex2(sigma * log2 e)))
-// lg2(1 + z) needs RELATIVE accuracy for tiny z (the last sample multiplies it by 1e10), so below
-// 1e-2 the series log2(e) * (z - z^2/2 + z^3/3) is used; above the softplus threshold (20) the
-// reference returns sigma itself.
-__device__ __forceinline__ float transmit_factor(float sigma, float delta) {
-  const float s2 = sigma * 1.4426950408889634f;
-  const float z = exp2f_approx(s2);
-  const float series = z * fmaf(z, fmaf(z, 0.4808983469629878f, -0.7213475204444817f), 1.4426950408889634f);
-  const float lg = lg2f_approx(1.f + z);
-  const float L = sigma > 20.f ? s2 : (z < 1e-2f ? series : lg);
-  return exp2f_approx(-L * delta);
 }
 
 template <int S>
@@ -210,9 +181,7 @@ __device__ __forceinline__ float dir_norm_fast(const float* __restrict__ dirs, i
   } else {
     const float2* q = reinterpret_cast<const float2*>(dirs + ray * 6);
     const float2 b = __ldg(q + 1), c = __ldg(q + 2);
-    float inv;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(c.y, c.y, fmaf(c.x, c.x, b.y * b.y))));   // :37
-    dx = b.y * inv; dy = c.x * inv; dz = c.y * inv;
+    return unit_dir_norm(b.y, c.x, c.y);
   }
   float n;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));              // :62

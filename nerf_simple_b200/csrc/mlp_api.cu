@@ -20,6 +20,9 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
 int tc_backward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
                 const float* d_out, const void* saved, float* const* G, void* scratch,
                 size_t scratch_bytes, cudaStream_t s);
+int tc_render(const float* rays, const float* poses, int H, int W, float f, int64_t ray_begin, const float* ts, uint64_t seed,
+              uint64_t offset, int64_t B, int N, float tn, float tf, const void* packed, float* rgb, float* disp, float* acc,
+              cudaStream_t s);
 }  // namespace nb200
 
 extern "C" {
@@ -92,6 +95,37 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
   if (!packed) return NB200_ERR_ARG;
   return nb200::tc_backward(in_mode, in0, in1, M, N, packed, d_out, saved, grads, scratch,
                             scratch_bytes, nb200::as_stream(stream));
+}
+
+static int check_render(int precision, int64_t B, int N, const void* packed, const float* rgb, const float* disp,
+                        const float* acc) {
+  if (precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;     // the fp32 parity mode keeps the three-kernel path
+  if (B < 0 || N < 2) return NB200_ERR_ARG;
+  if (N != 32 && N != 64 && N != 128) return NB200_ERR_UNSUPPORTED;  // whole rays per 128-sample tile
+  if (B > 0 && (!packed || !rgb || !disp || !acc)) return NB200_ERR_ARG;
+  return NB200_OK;
+}
+
+int nb200_render_rays(int precision, const float* rays, const float* ts, uint64_t seed, uint64_t offset, int64_t B, int N,
+                      float tn, float tf, const void* packed, float* rgb, float* disp, float* acc, nb200_stream_t stream) {
+  int rc = check_render(precision, B, N, packed, rgb, disp, acc);
+  if (rc != NB200_OK) return rc;
+  if (B == 0) return NB200_OK;
+  if (!rays || ((uintptr_t)rays & 7)) return NB200_ERR_ARG;
+  return nb200::tc_render(rays, nullptr, 0, 0, 0.f, 0, ts, seed, offset, B, N, tn, tf, packed, rgb, disp, acc,
+                          nb200::as_stream(stream));
+}
+
+int nb200_render_camera(int precision, const float* poses, int P, int H, int W, float f, int64_t ray_begin, int64_t n_rays,
+                        uint64_t seed, uint64_t offset, int N, float tn, float tf, const void* packed, float* rgb,
+                        float* disp, float* acc, nb200_stream_t stream) {
+  int rc = check_render(precision, n_rays, N, packed, rgb, disp, acc);
+  if (rc != NB200_OK) return rc;
+  if (P <= 0 || H <= 0 || W <= 0 || !(f > 0.f) || ray_begin < 0 || ray_begin + n_rays > (int64_t)P * H * W) return NB200_ERR_ARG;
+  if (n_rays == 0) return NB200_OK;
+  if (!poses) return NB200_ERR_ARG;
+  return nb200::tc_render(nullptr, poses, H, W, f, ray_begin, nullptr, seed, offset, n_rays, N, tn, tf, packed, rgb, disp, acc,
+                          nb200::as_stream(stream));
 }
 
 }  // extern "C"

@@ -256,28 +256,124 @@ struct FwdEpiParams {
   const float* in1;
   int64_t M;
   int N;
+  int nshift;      // log2(N) when N is a power of two, else -1 (sample -> ray index without a 64-bit division)
   const uint8_t* packed;
   float* out;
   uint8_t* saved;  // null for inference
   int64_t num_tiles;
+  // fused render (FwdEpi<false, true>): sampler -> MLP -> compositing in one kernel, N in {32, 64, 128}
+  float* rgb;        // [B,3]
+  float* disp;       // [B]
+  float* acc;        // [B]
+  int64_t B;
+  int sampler;       // 0: sample depths from in1 [B,N]; 1: Philox(seed, offset) like stratified_ts_quad_kernel
+  uint64_t seed, offset;
+  float tn, tf;
+  const float* poses;  // in_mode == kInCamera: rays come from (poses [P,4,4], H, W, f, ray_begin + ray)
+  int H, W;
+  float f;
+  int64_t ray_begin;
 };
+constexpr int kInCamera = 2;  // internal input mode of the fused render kernel
 
-__device__ __forceinline__ void load_query_chain(const FwdEpiParams& p, int64_t m, float v[6]) {
-  if (p.in_mode == NB200_IN_POINTS) {
+// (origin, direction) of ray `ray`: a row of the rays tensor, or generated from the camera
+__device__ __forceinline__ void load_ray_chain(const FwdEpiParams& p, int64_t ray, float (&o)[6]) {
+  if (p.in_mode == kInCamera) {
+    camera_ray(p.poses, p.H, p.W, p.f, p.ray_begin + ray, o);
+  } else {
+    const float2* q = reinterpret_cast<const float2*>(p.in0 + ray * 6);
+    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
+  }
+}
+
+template <bool kRender>
+__device__ __forceinline__ void load_query_chain(const FwdEpiParams& p, int64_t m, float v[6], float& t) {
+  if (!kRender && p.in_mode == NB200_IN_POINTS) {
     const float2* q = reinterpret_cast<const float2*>(p.in0 + m * 6);
     const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+    t = 0.f;
   } else {
-    const int64_t ray = m / p.N;
-    const float2* q = reinterpret_cast<const float2*>(p.in0 + ray * 6);
-    const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    const float t = __ldg(p.in1 + m);
-    const float dx = b.y, dy = c.x, dz = c.y;
-    v[0] = __fadd_rn(a.x, __fmul_rn(dx, t));  // utils/rendering.py:34-36 (d un-normalised)
-    v[1] = __fadd_rn(a.y, __fmul_rn(dy, t));
-    v[2] = __fadd_rn(b.x, __fmul_rn(dz, t));
+    const int64_t ray = p.nshift >= 0 ? (m >> p.nshift) : m / p.N;
+    float o[6];
+    if (kRender) {
+      load_ray_chain(p, ray, o);
+      t = p.sampler ? philox_sample_depth(m, (int)(m - ray * p.N), p.N, p.tn, p.tf, p.seed, p.offset) : __ldg(p.in1 + m);
+    } else {
+      const float2* q = reinterpret_cast<const float2*>(p.in0 + ray * 6);
+      const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
+      t = __ldg(p.in1 + m);
+    }
+    const float dx = o[3], dy = o[4], dz = o[5];
+    v[0] = __fadd_rn(o[0], __fmul_rn(dx, t));  // utils/rendering.py:34-36 (d un-normalised)
+    v[1] = __fadd_rn(o[1], __fmul_rn(dy, t));
+    v[2] = __fadd_rn(o[2], __fmul_rn(dz, t));
     const float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));  // :37
     v[3] = dx * inv; v[4] = dy * inv; v[5] = dz * inv;
+  }
+}
+
+// Fused render: composite one ray of the tile from the (r,g,b,sigma) / depth rows staged in shared
+// memory.  One warp, lane l owns the S = N/32 consecutive samples l*S..l*S+S-1: the same arithmetic,
+// in the same order, as composite_fwd_kernel<S, ., ., true, false, 1> (utils/rendering.py:60-83).
+template <int S>
+__device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint32_t stage_o, uint32_t stage_t, int ray_local,
+                                                     int64_t ray, int lane) {
+  constexpr int N = 32 * S;
+  float4 o[S];
+  float t[S];
+  const uint32_t row0 = (uint32_t)(ray_local * N + lane * S);
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[j].x), "=f"(o[j].y), "=f"(o[j].z), "=f"(o[j].w) : "r"(stage_o + (row0 + j) * 16u));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t[j]) : "r"(stage_t + (row0 + j) * 4u));
+  }
+  float rd[6];
+  load_ray_chain(p, ray, rd);
+  const float norm = unit_dir_norm(rd[3], rd[4], rd[5]);
+  const float t_next_lane = __shfl_down_sync(0xffffffffu, t[0], 1);
+  float a[S], pre[S];
+  float run = 1.f;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const bool last = (j == S - 1 && lane == 31);
+    const float tn = (j == S - 1) ? t_next_lane : t[j + 1 < S ? j + 1 : j];
+    const float d = last ? 1e10f : __fsub_rn(tn, t[j]);                             // :60-61
+    const float delta = __fmul_rn(d, norm);                                         // :62
+    const float e = transmit_factor(o[j].w, delta);                                 // :67
+    a[j] = __fsub_rn(1.f, e);
+    const float fac = __fadd_rn(__fsub_rn(1.f, a[j]), 1e-10f);                      // :68
+    pre[j] = run;
+    run *= fac;
+  }
+  float pr = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, pr, d);
+    pr *= (lane >= d) ? v : 1.f;
+  }
+  float ex = __shfl_up_sync(0xffffffffu, pr, 1);
+  ex = lane == 0 ? 1.f : ex;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const float w = a[j] * (ex * pre[j]);
+    sr = fmaf(w, o[j].x, sr); sg = fmaf(w, o[j].y, sg); sb = fmaf(w, o[j].z, sb);
+    sd = fmaf(w, t[j], sd);
+    sa += w;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, d); sg += __shfl_xor_sync(0xffffffffu, sg, d);
+    sb += __shfl_xor_sync(0xffffffffu, sb, d); sd += __shfl_xor_sync(0xffffffffu, sd, d);
+    sa += __shfl_xor_sync(0xffffffffu, sa, d);
+  }
+  if (lane == 0) {
+    p.rgb[ray * 3] = sr; p.rgb[ray * 3 + 1] = sg; p.rgb[ray * 3 + 2] = sb;
+    p.disp[ray] = disparity(sd, sa);
+    p.acc[ray] = sa;
   }
 }
 
@@ -336,8 +432,9 @@ __device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8
   }
 }
 
-template <bool kSave>
+template <bool kSave, bool kRender = false>
 struct FwdEpi {
+  static_assert(!(kSave && kRender), "the fused render kernel is inference only");
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
@@ -345,6 +442,7 @@ struct FwdEpi {
   struct State {
     float v[6];
     float sigma;
+    float t;          // sample depth (fused render)
     int64_t m_raw;
     bool row_valid;
   };
@@ -355,7 +453,7 @@ struct FwdEpi {
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
     st.m_raw = c.tile * kTileM + c.r;
     st.row_valid = st.m_raw < p.M;
-    load_query_chain(p, st.row_valid ? st.m_raw : p.M - 1, st.v);
+    load_query_chain<kRender>(p, st.row_valid ? st.m_raw : p.M - 1, st.v, st.t);
     st.sigma = 0.f;
     // posx -> E[slot] (K = 64); each half of the slot's threads stores 4 of the 8 16-byte chunks
     if (c.half == 0) encode_row<kLp, 0, 4>(st.v, c.e_img, c.r, nullptr);
@@ -417,12 +515,29 @@ struct FwdEpi {
       if (c.half == 0) {
         float4 o;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xaddr));
-        if (st.row_valid)
-          reinterpret_cast<float4*>(p.out)[st.m_raw] =
-              make_float4(rgb[0] + o.x + c_f32[kF32BC1], rgb[1] + o.y + c_f32[kF32BC1 + 1], rgb[2] + o.z + c_f32[kF32BC1 + 2],
-                          st.sigma + o.w + c_f32[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
+        const float4 res = make_float4(rgb[0] + o.x + c_f32[kF32BC1], rgb[1] + o.y + c_f32[kF32BC1 + 1], rgb[2] + o.z + c_f32[kF32BC1 + 2],
+                                       st.sigma + o.w + c_f32[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
+        if (kRender) {
+          // stage the row for the compositing warps in A[slot]: its last reader (color_fc.0's MMAs) is done and
+          // the next writer (layer 0's epilogue of the next tile) runs only after every warp of the slot has
+          // arrived for that tile, i.e. after the compositing below
+          st_shared_v4(c.a_img + c.r * 16u, __float_as_uint(res.x), __float_as_uint(res.y), __float_as_uint(res.z), __float_as_uint(res.w));
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.a_img + 2048u + c.r * 4u), "f"(st.t) : "memory");
+        } else if (st.row_valid) {
+          reinterpret_cast<float4*>(p.out)[st.m_raw] = res;
+        }
       }
       slot_barrier(c.slot);  // E[slot] may be re-encoded for the next tile only after the exchange was read
+      if (kRender) {
+        const int wq = (int)(threadIdx.x >> 5) & 7, nr = kTileM / p.N;   // warp wq composites ray wq of the tile
+        const int64_t ray = c.tile * nr + wq;
+        if (wq < nr && ray < p.B) {
+          const int lane = (int)threadIdx.x & 31;
+          if (p.N == 64) composite_staged_ray<2>(p, c.a_img, c.a_img + 2048u, wq, ray, lane);
+          else if (p.N == 128) composite_staged_ray<4>(p, c.a_img, c.a_img + 2048u, wq, ray, lane);
+          else composite_staged_ray<1>(p, c.a_img, c.a_img + 2048u, wq, ray, lane);
+        }
+      }
     }
   }
 };

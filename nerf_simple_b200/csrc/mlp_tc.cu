@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "stream_common.cuh"
 #include "tc_common.cuh"
 
 namespace nb200 {
@@ -336,6 +337,7 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
     p.dbg_counters = ctr;
   }
   p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
+  p.nshift = (N > 0 && (N & (N - 1)) == 0) ? __builtin_ctz((unsigned)N) : -1;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
   p.num_tiles = T;
@@ -345,6 +347,39 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   else
     chain_kernel<FwdEpi<false>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
   NB_LAUNCH_CHECK("chain_kernel<FwdEpi>");
+  return NB200_OK;
+}
+
+// Fused render: sampler -> posenc + MLP -> compositing in ONE kernel; per-sample (r,g,b,sigma) and the
+// sample depths never reach HBM.  rays == nullptr: rays are generated from (poses, H, W, f, ray_begin).
+// ts == nullptr: Philox sample depths (same stream as nb200_stratified_ts with the same seed/offset).
+int tc_render(const float* rays, const float* poses, int H, int W, float f, int64_t ray_begin, const float* ts, uint64_t seed,
+              uint64_t offset, int64_t B, int N, float tn, float tf, const void* packed, float* rgb, float* disp, float* acc,
+              cudaStream_t s) {
+  NB_TRY_RC(check_arch());
+  NB_TRY_RC(ensure_layout());
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
+    attr_set = true;
+  }
+  const int64_t M = B * N, T = ceil_div64(M, kTileM);
+  NB_TRY_RC(upload_consts(packed, s));
+  const TmapPair* tm = nullptr;
+  NB_TRY_RC(get_tmaps(packed, &tm));
+  FwdEpiParams p;
+  memset(&p, 0, sizeof(p));
+  p.tmap128 = tm->m128; p.tmap64 = tm->m64;
+  p.in_mode = rays ? NB200_IN_RAYS : kInCamera; p.in0 = rays; p.in1 = ts; p.M = M; p.N = N;
+  p.nshift = (N > 0 && (N & (N - 1)) == 0) ? __builtin_ctz((unsigned)N) : -1;
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.num_tiles = T;
+  p.rgb = rgb; p.disp = disp; p.acc = acc; p.B = B;
+  p.sampler = ts ? 0 : 1; p.seed = seed; p.offset = offset; p.tn = tn; p.tf = tf;
+  p.poses = poses; p.H = H; p.W = W; p.f = f; p.ray_begin = ray_begin;
+  chain_kernel<FwdEpi<false, true>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(p);
+  NB_LAUNCH_CHECK("chain_kernel<FwdEpi<render>>");
   return NB200_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "stream_common.cuh"
 
 namespace nb200 {
 
@@ -13,27 +14,10 @@ namespace nb200 {
 __global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restrict__ poses, int H,
                                                             int W, float f, int64_t ray_begin,
                                                             int64_t n_rays, float* __restrict__ rays) {
-  const int64_t hw = (int64_t)H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = ray_begin + i;
-    const int64_t p = r / hw;
-    const int64_t pix = r - p * hw;
-    const int h = (int)(pix / W), w = (int)(pix - (int64_t)h * W);
-    // utils/xyz.py:46-49: integer centre, (gx/f, -gy/f, -1); IEEE division like torch.
-    const float dx = __fdiv_rn((float)(w - W / 2), f);
-    const float dy = -__fdiv_rn((float)(h - H / 2), f);
-    const float dz = -1.0f;
-    const float* T = poses + p * 16;
     float o[6];
-    o[0] = __ldg(T + 3);
-    o[1] = __ldg(T + 7);
-    o[2] = __ldg(T + 11);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      // utils/rendering.py:131: transf_mats[:, :3, :3] @ rays_1_cam
-      o[3 + a] = fmaf(__ldg(T + 4 * a + 2), dz, fmaf(__ldg(T + 4 * a + 1), dy, __ldg(T + 4 * a) * dx));
-    }
+    camera_ray(poses, H, W, f, ray_begin + i, o);
     float2* dst = reinterpret_cast<float2*>(rays + i * 6);  // 24 B rows are 8 B aligned
     dst[0] = make_float2(o[0], o[1]);
     dst[1] = make_float2(o[2], o[3]);
@@ -42,37 +26,6 @@ __global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restr
 }
 
 // --------------------------------------------------------------------------------- sampler
-__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
-  *hi = __umulhi(a, b);
-  return a * b;
-}
-
-// Philox4x32-10 (Salmon et al. 2011): counter = (ctr lo, ctr hi, 0, 0), key = seed.
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t seed) {
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0, hi1;
-    const uint32_t lo0 = mulhilo32(0xD2511F53u, c0, &hi0);
-    const uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, &hi1);
-    c0 = hi1 ^ c1 ^ k0;
-    c1 = lo1;
-    c2 = hi0 ^ c3 ^ k1;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
-
-// torch.linspace(tn, tf, N+1)[i] in fp32 (symmetric two-sided fma evaluation).
-__device__ __forceinline__ float tbin(int i, int N, float tn, float tf, float step) {
-  return (i < (N + 1) / 2) ? fmaf(step, (float)i, tn) : fmaf(-step, (float)(N - i), tf);
-}
-
 // Each thread produces 4 consecutive samples (one Philox call, one 16 B store when aligned).
 __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restrict__ u, uint64_t seed,
                                                             uint64_t offset, int64_t total, int N,

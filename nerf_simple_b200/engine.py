@@ -1,8 +1,10 @@
 """Device-resident drivers of the hot path: what bench.py and the multi-GPU entry points call.
 
-`FrameRenderer` renders whole novel views (the loop of utils/rendering.py:139-151) with rays
-generated on the device, Philox jitter, the fused MLP kernel and the compositing kernel: four
-launches per frame, no per-chunk host traffic.  `shard_range` / `render_sharded` split the rays
+`FrameRenderer` renders whole novel views (the loop of utils/rendering.py:139-151).  Coarse-only
+frames with N in {32, 64, 128} are ONE kernel launch: rays from the camera, Philox jitter, the
+tcgen05 MLP chain and the compositing all happen inside chain_kernel<FwdEpi<render>>, so neither
+rays, sample depths nor per-sample (r,g,b,sigma) touch HBM.  Other shapes (and `fused=False`) use
+the four separate kernels: ray generation, sampler, fused MLP, compositing.  `shard_range` / `render_sharded` split the rays
 of a frame across ranks with one final gather.
 """
 from __future__ import annotations
@@ -20,11 +22,12 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class FrameRenderer:
-    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None, net_fine=None, Nf=0):
+    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None, net_fine=None, Nf=0, fused=True):
         self.net, self.H, self.W, self.f, self.N = net, int(H), int(W), float(f), int(N)
         self.net_fine, self.Nf = net_fine, int(Nf)   # hierarchical extension: N coarse + Nf fine samples
         self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
         self.precision = precision
+        self.fused = bool(fused) and net_fine is None and ops.fused_render_supported(net, N, precision)
         self.device = next(net.parameters()).device
         self._offset = 0
         self.launches = 0          # kernels of libnerf_b200 launched so far
@@ -34,6 +37,19 @@ class FrameRenderer:
         """rgb [n,3] clipped to [0,1] and disparity [n] for rays [ray_begin, ray_begin+n) of the
         pose table `poses_dev` ([P,4,4] on the device)."""
         with torch.no_grad():
+            if self.fused:
+                if time_mlp:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                rgb, disp, _ = ops.render_fused(self.net, self.N, poses=poses_dev, H=self.H, W=self.W, f=self.f,
+                                                ray_begin=ray_begin, n_rays=n_rays, tn=self.tn, tf=self.tf,
+                                                seed=self.seed, offset=self._offset)
+                if time_mlp:
+                    e1.record()
+                    self.mlp_events.append((e0, e1))
+                self._offset += (n_rays * self.N + 3) // 4
+                self.launches += 1
+                return rgb.clamp_(0.0, 1.0), disp
             rays = ops.generate_rays(poses_dev, self.H, self.W, self.f, ray_begin, n_rays)
             ts = ops.stratified_ts(n_rays, self.N, self.tn, self.tf, device=self.device, seed=self.seed,
                                    offset=self._offset)

@@ -234,6 +234,56 @@ def generate_rays(poses, H, W, f, ray_begin=0, n_rays=None):
     return rays
 
 
+# ----------------------------------------------------------------------------- fused render
+FUSED_RENDER_N = (32, 64, 128)     # whole rays per 128-sample tile
+
+
+def fused_render_supported(net, N, precision=None) -> bool:
+    precision = precision or getattr(net, "precision", None) or config.get_precision()
+    return precision == "bf16" and int(N) in FUSED_RENDER_N
+
+
+def render_fused(net, N, rays=None, ts=None, poses=None, H=0, W=0, f=0.0, ray_begin=0, n_rays=None,
+                 tn=2.0, tf=6.0, seed=None, offset=None):
+    """No-grad render_nerf (utils/rendering.py:13-45) as ONE kernel: sampler -> posenc + MLP -> compositing.
+    Either `rays` [B,6] (optionally with `ts` [B,N]; else Philox depths keyed by (seed, offset)), or a
+    camera (`poses` [P,4,4], H, W, f, ray_begin, n_rays) whose rays are generated in the kernel.
+    Returns (rgb [B,3], disp [B], acc [B]); equals stratified_ts + mlp_apply + composite_apply."""
+    lib = _lib.load()
+    params = net.kernel_params()
+    _lib.require_cuda(params[0], "Nerf parameters (call net.cuda())")
+    dev = params[0].device
+    packed = net._packed.get(params, _lib.BF16)
+    if rays is not None:
+        rays = _f32c(rays, "rays")
+        B = rays.shape[0]
+        if ts is not None:
+            ts = _f32c(ts, "ts")
+            if ts.shape != (B, N):
+                raise ValueError(f"ts must be [B,N]; got {tuple(ts.shape)}")
+    else:
+        poses = _f32c(poses, "poses")
+        if poses.dim() == 2:
+            poses = poses[None]
+        B = int(n_rays if n_rays is not None else poses.shape[0] * H * W - ray_begin)
+    if ts is None and seed is None:
+        seed, offset = config.next_philox(B * N)
+    rgb = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    disp = torch.empty((B,), dtype=torch.float32, device=dev)
+    acc = torch.empty((B,), dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr(dev)
+    if rays is not None:
+        rc = lib.nb200_render_rays(_lib.BF16, _lib.ptr(rays), _lib.ptr(ts), int(seed or 0), int(offset or 0), B, int(N),
+                                   float(tn), float(tf), _lib.ptr(packed), _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), st)
+        _lib.check(rc, "nb200_render_rays")
+    else:
+        rc = lib.nb200_render_camera(_lib.BF16, _lib.ptr(poses), poses.shape[0], int(H), int(W), float(f), int(ray_begin), B,
+                                     int(seed or 0), int(offset or 0), int(N), float(tn), float(tf), _lib.ptr(packed),
+                                     _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), st)
+        _lib.check(rc, "nb200_render_camera")
+    return rgb, disp, acc
+
+
 def positional_encoding(v, Lp=10, Ld=4):
     lib = _lib.load()
     v = _f32c(v, "vec")

@@ -37,14 +37,29 @@ def volume_render(nerf_outs, ts, dirs):
     return ops.composite_apply(nerf_outs, ts, dirs, dirs_mode=0)
 
 
+def _render_chunk(chunk, net, N):
+    """(rgb, disparity) of one no-grad chunk: the single fused kernel when the shape allows it (bf16,
+    N in {32,64,128}), else render_nerf's three kernels.  Same sampler semantics as render_nerf."""
+    if not ops.fused_render_supported(net, N):
+        rgb, depth, _, _, _ = render_nerf(chunk, net, N=N)
+        return rgb, depth
+    if config.get_sampler() == "reference":
+        u = torch.rand(chunk.size(0), N)                       # utils/rendering.py:28, CPU global generator
+        ts = ops.stratified_ts(chunk.size(0), N, 2, 6, u=u.to(chunk.device, non_blocking=True))
+        rgb, depth, _ = ops.render_fused(net, N, rays=chunk, ts=ts)
+    else:
+        rgb, depth, _ = ops.render_fused(net, N, rays=chunk)
+    return rgb, depth
+
+
 def _render_chunks(net, rays, batch_size, N=128):
     """Chunked no-grad render of a ray table; unlike :100,:143 the remainder chunk is kept."""
     rgbs, depths = [], []
     dev = next(net.parameters()).device
     with torch.no_grad():
         for s in range(0, rays.size(0), batch_size):
-            chunk = rays[s:s + batch_size].to(dev, non_blocking=True)
-            rgb, depth, _, _, _ = render_nerf(chunk, net, N=N)
+            chunk = rays[s:s + batch_size].to(dev, non_blocking=True).float().contiguous()
+            rgb, depth = _render_chunk(chunk, net, N)
             rgbs.append(rgb.clamp_(0.0, 1.0))       # :103,:146
             depths.append(depth)
     return torch.cat(rgbs), torch.cat(depths)
@@ -79,8 +94,11 @@ def render_poses(net, poses, cam_params, batch_size, savepath=''):
             rgbs, depths = [], []
             for s in range(0, n, batch_size):
                 cnt = min(batch_size, n - s)
-                rays = ops.generate_rays(pose_t, H, W, f, ray_begin=idx * n + s, n_rays=cnt)
-                rgb, depth, _, _, _ = render_nerf(rays, net, N=128)
+                if ops.fused_render_supported(net, 128) and config.get_sampler() == "philox":
+                    rgb, depth, _ = ops.render_fused(net, 128, poses=pose_t, H=H, W=W, f=f, ray_begin=idx * n + s, n_rays=cnt)
+                else:
+                    rays = ops.generate_rays(pose_t, H, W, f, ray_begin=idx * n + s, n_rays=cnt)
+                    rgb, depth = _render_chunk(rays, net, 128)
                 rgbs.append(rgb.clamp_(0.0, 1.0))
                 depths.append(depth)
             frames.append(torch.cat(rgbs).reshape(H, W, 3).cpu().numpy())

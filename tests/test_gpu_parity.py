@@ -304,3 +304,60 @@ def test_edge_shapes(net, precision):
         assert alpha.shape == (77, 37) and bool(torch.isfinite(rgb).all()) and float((acc - 1).abs().max()) <= 1e-4
     with pytest.raises(ValueError):
         volume_render(torch.zeros(2, 1, 4, device="cuda"), torch.zeros(2, 1, device="cuda"), torch.zeros(2, 3, device="cuda"))
+
+
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_fused_render_equals_three_kernels(N):
+    """nb200_render_rays / nb200_render_camera (sampler -> MLP -> compositing in one kernel) against the
+    three separate kernels on the same inputs, and against the oracle on the golden case."""
+    from nerf_simple_b200 import ops, _lib
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.xyz import poses_to_render
+    torch.manual_seed(0)
+    net = Nerf().cuda()
+    net.precision = "bf16"
+    poses = torch.stack(poses_to_render(4, -30, 3)).cuda()
+    H = W = 40
+    f = 55.5
+    with torch.no_grad():
+        for ray_begin, B in ((0, 77), (1000, 1024), (3 * H * W - 130, 130)):       # ragged tails, last rays of the table
+            rays = ops.generate_rays(poses, H, W, f, ray_begin, B)
+            # (a) supplied sample depths (reference-RNG mode)
+            ts = ops.stratified_ts(B, N, 2, 6, u=torch.rand(B, N).cuda())
+            out = ops.mlp_apply(net, _lib.IN_RAYS, rays, ts, N).view(B, N, 4)
+            rgb0, disp0, acc0 = ops.composite_apply(out, ts, rays, dirs_mode=1, want_alpha_weights=False)
+            rgb1, disp1, acc1 = ops.render_fused(net, N, rays=rays, ts=ts)
+            assert maxabs(rgb1, rgb0) <= 1e-6 and maxabs(acc1, acc0) <= 1e-6
+            assert float(((disp1 - disp0).abs() / disp0.abs().clamp_min(1e-6)).max()) <= 1e-5
+            # (b) Philox depths generated in the kernel == the sampler kernel's stream
+            ts_p = ops.stratified_ts(B, N, 2, 6, device="cuda", seed=11, offset=5)
+            out = ops.mlp_apply(net, _lib.IN_RAYS, rays, ts_p, N).view(B, N, 4)
+            rgb0, disp0, acc0 = ops.composite_apply(out, ts_p, rays, dirs_mode=1, want_alpha_weights=False)
+            rgb1, disp1, acc1 = ops.render_fused(net, N, rays=rays, seed=11, offset=5)
+            assert maxabs(rgb1, rgb0) <= 1e-6 and maxabs(acc1, acc0) <= 1e-6
+            # (c) rays generated in the kernel from the camera
+            rgb2, disp2, acc2 = ops.render_fused(net, N, poses=poses, H=H, W=W, f=f, ray_begin=ray_begin, n_rays=B,
+                                                 seed=11, offset=5)
+            assert torch.equal(rgb2, rgb1) and torch.equal(disp2, disp1) and torch.equal(acc2, acc1)
+    # unsupported shapes are refused, not silently mis-rendered
+    lib = _lib.load()
+    z = torch.zeros(8, 6, device="cuda")
+    o = torch.zeros(8, 3, device="cuda")
+    rc = lib.nb200_render_rays(_lib.BF16, _lib.ptr(z), None, 0, 0, 8, 48, 2.0, 6.0, _lib.ptr(net._packed.get(net.kernel_params(), _lib.BF16)),
+                               _lib.ptr(o), _lib.ptr(o), _lib.ptr(o), _lib.stream_ptr())
+    assert rc == -2
+    assert not ops.fused_render_supported(net, 48) and not ops.fused_render_supported(net, 64, "fp32")
+
+
+def test_fused_render_golden(net):
+    """The fused kernel against the reference-generated golden render (bf16 tolerance of the north star)."""
+    from nerf_simple_b200 import ops, config
+    config.set_precision("bf16")
+    g = load_golden("case_render_b1024_n64.npz")
+    rays = torch.from_numpy(g["rays"]).cuda()
+    with torch.no_grad():
+        ts = ops.stratified_ts(1024, 64, 2, 6, u=torch.from_numpy(g["u"]).cuda())
+        rgb, disp, acc = ops.render_fused(net, 64, rays=rays, ts=ts)
+    assert maxabs(rgb, g["rgb"]) <= 1e-2 and maxabs(acc, g["acc"]) <= 1e-2
+    mse = float(((rgb.cpu() - torch.from_numpy(g["rgb"])) ** 2).mean())
+    assert 10 * np.log10(1.0 / max(mse, 1e-20)) > 60
