@@ -15,6 +15,10 @@
 #include "stream_common.cuh"
 #include "tc_common.cuh"
 
+#ifndef NB_WG_OVH
+#define NB_WG_OVH 48
+#endif
+
 namespace nb200 {
 using namespace tc;
 
@@ -452,9 +456,10 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   item(7, 1, L0_2, kHidden, 0, kHidden, kHidden, true);
   item(8, 0, L0_1, kHidden, 0, kHidden, kHidden, true);
   item(9, 10, L0_0, kPosX, 0, kPosX, kHidden, true);                        // layers_0.0 <- posx
-  // measured: a 32-row stage costs a fixed latency share on top of its bytes (the 6-stage ring is
-  // latency-bound for small stages); 96 'KB-equivalents' per tile balances the CTAs best (sweep 0..384)
-  for (int i = 0; i < n; ++i) wp.items[i].cost += 96;
+  // measured: a stage costs a fixed latency share on top of its bytes (items with small stages are
+  // latency-bound in the ring); NB_WG_OVH 'KB-equivalents' per tile balance the CTAs (sweeps: 96 was
+  // best with 32-row stages, 32..64 equivalent with 64-row stages)
+  for (int i = 0; i < n; ++i) wp.items[i].cost += NB_WG_OVH;
   wp.num_items = n;
   mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");

@@ -75,9 +75,18 @@ struct WgradParams {
   const float* d_out;     // [M,4] cotangent of (r,g,b,sigma): the head "deltas"
 };
 
-constexpr int kWgStages = 6;  // (an extra L2 prefetch ahead of the ring was measured: 548 -> 742 us, so there is none)
-constexpr uint32_t kWgStageData = 32768;   // 32 sample rows: A chunks 4 x 4 KB | B chunks 4 x 4 KB
-constexpr uint32_t kWgStageBytes = kWgStageData + 1024;  // + d_out rows of the stage (512 B) for the head items
+// A stage holds kWgRows sample rows of up to 4 A chunks and 4 B chunks (64 features x kWgRows x 2 B each).
+// (An extra L2 prefetch ahead of the ring was measured: 548 -> 742 us, so there is none.)
+#ifndef NB_WG_ROWS
+#define NB_WG_ROWS 64
+#endif
+constexpr int kWgRows = NB_WG_ROWS;                      // 32 or 64
+constexpr int kWgSubs = kTileM / kWgRows;                // stages per 128-sample tile
+constexpr int kWgStages = 192 / kWgRows;                 // 6 x 32 KB or 3 x 64 KB in flight
+constexpr uint32_t kWgChunk = kWgRows * 128u;            // one 64-feature chunk of a stage
+constexpr uint32_t kWgHalf = 4u * kWgChunk;              // A region; the B region follows
+constexpr uint32_t kWgStageData = 2u * kWgHalf;
+constexpr uint32_t kWgStageBytes = kWgStageData + 1024;  // + d_out rows of the stage (16 B each) for the head items
 constexpr uint32_t kWgSmemBar = kWgStages * kWgStageBytes;  // 196608
 constexpr uint32_t kWgSmemLaunch = kWgSmemBar + 256 + 1024;
 constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 bias sums + flush
@@ -134,24 +143,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
         const WItem& w = p.items[it];
         const int64_t tb = (it == i0) ? t0 : 0, te = (it == i1) ? t1 : p.T;
         for (int64_t tile = tb; tile < te; ++tile) {
-          for (int sub = 0; sub < 4; ++sub) {
+          for (int sub = 0; sub < kWgSubs; ++sub) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 900);
             // head items also stage the 32 d_out rows (the global-load latency under a saturated HBM is
             // several stage periods, so they have to travel with the stage)
-            const int64_t m0 = tile * kTileM + sub * 32;
-            const uint32_t g_bytes = !w.head || m0 >= p.M ? 0u : (uint32_t)((p.M - m0 < 32 ? p.M - m0 : 32) * 16);
-            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(w.a_chunks + w.b_chunks + w.x_chunks) * 4096u + g_bytes);
+            const int64_t m0 = tile * kTileM + sub * kWgRows;
+            const uint32_t g_bytes = !w.head || m0 >= p.M ? 0u : (uint32_t)((p.M - m0 < kWgRows ? p.M - m0 : kWgRows) * 16);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(w.a_chunks + w.b_chunks + w.x_chunks) * kWgChunk + g_bytes);
             const uint32_t dst = smem_base + stage * kWgStageBytes;
             if (g_bytes) tma_bulk_g2s(dst + kWgStageData, p.d_out + m0 * 4, g_bytes, bar_full + 8 * stage);
             for (int c = 0; c < w.a_chunks; ++c)
-              tma_bulk_g2s(dst + c * 4096, w.a_ptr + (size_t)tile * w.a_tile_bytes + c * 16384 + sub * 4096, 4096,
+              tma_bulk_g2s(dst + c * kWgChunk, w.a_ptr + (size_t)tile * w.a_tile_bytes + c * 16384 + sub * kWgChunk, kWgChunk,
                            bar_full + 8 * stage);
             for (int c = 0; c < w.b_chunks; ++c)
-              tma_bulk_g2s(dst + 16384 + c * 4096, w.b_ptr + (size_t)tile * w.b_tile_bytes + c * 16384 + sub * 4096,
-                           4096, bar_full + 8 * stage);
+              tma_bulk_g2s(dst + kWgHalf + c * kWgChunk, w.b_ptr + (size_t)tile * w.b_tile_bytes + c * 16384 + sub * kWgChunk,
+                           kWgChunk, bar_full + 8 * stage);
             for (int c = 0; c < w.x_chunks; ++c)
-              tma_bulk_g2s(dst + 16384 + (w.b_chunks + c) * 4096, w.x_ptr + (size_t)tile * w.x_tile_bytes + c * 16384 + sub * 4096,
-                           4096, bar_full + 8 * stage);
+              tma_bulk_g2s(dst + kWgHalf + (w.b_chunks + c) * kWgChunk, w.x_ptr + (size_t)tile * w.x_tile_bytes + c * 16384 + sub * kWgChunk,
+                           kWgChunk, bar_full + 8 * stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -171,15 +180,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
         const int halves = w.a_chunks >> 1;
         bool first = true;
         for (int64_t tile = tb; tile < te; ++tile) {
-          for (int sub = 0; sub < 4; ++sub) {
+          for (int sub = 0; sub < kWgSubs; ++sub) {
             mbar_wait(bar_full + 8 * stage, phase, 1100);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * kWgStageBytes;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {  // 16 sample rows per MMA
-              const uint64_t bdesc = umma_smem_desc(sa + 16384 + ks * 2048, 4096, 1024);
+            for (int ks = 0; ks < kWgRows / 16; ++ks) {  // 16 sample rows per MMA
+              const uint64_t bdesc = umma_smem_desc(sa + kWgHalf + ks * 2048, kWgChunk, 1024);
               for (int h = 0; h < halves; ++h)
-                umma_bf16(tmem_base + h * 256, umma_smem_desc(sa + h * 8192 + ks * 2048, 4096, 1024), bdesc, idesc,
+                umma_bf16(tmem_base + h * 256, umma_smem_desc(sa + h * 2 * kWgChunk + ks * 2048, kWgChunk, 1024), bdesc, idesc,
                           (first && ks == 0) ? 0u : 1u);
             }
             first = false;
@@ -205,12 +214,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
       float4 hbias = make_float4(0.f, 0.f, 0.f, 0.f);
       const int head = w.head;
       for (int64_t tile = tb; tile < te; ++tile) {
-        for (int sub = 0; sub < 4; ++sub) {
+        for (int sub = 0; sub < kWgSubs; ++sub) {
           mbar_wait(bar_full + 8 * stage, phase, 1200);
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);      // d_out row `lane` of this 32-row stage
-          const uint32_t g_smem = smem_base + stage * kWgStageBytes + kWgStageData;
+#pragma unroll 1
+          for (int r32 = 0; r32 < kWgRows; r32 += 32) {     // 32 sample rows at a time (lane <-> row for d_out)
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);      // d_out row `lane` of these 32 rows
+          const uint32_t g_smem = smem_base + stage * kWgStageBytes + kWgStageData + r32 * 16;
+          const uint32_t rows_smem = smem_base + stage * kWgStageBytes + r32 * 128;
           if (head) {
-            if (tile * kTileM + sub * 32 + lane < p.M)
+            if (tile * kTileM + sub * kWgRows + r32 + lane < p.M)
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
                            : "r"(g_smem + lane * 16));
             else  // tail of the last tile: rows >= M were not copied; every warp zeroes them for its own reads
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
             hbias.x += g.x; hbias.y += g.y; hbias.z += g.z; hbias.w += g.w;
           }
           if (do_bias) {
-            const uint32_t base = smem_base + stage * kWgStageBytes + cw * 4096 + (lane & 3) * 4;
+            const uint32_t base = rows_smem + cw * kWgChunk + (lane & 3) * 4;
 #pragma unroll 8
             for (int row = 0; row < 32; ++row) {
               uint32_t v;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
           }
           if (head == 1) {
             // warp cw: columns [64 cw, 64 cw + 64) of h7; the d_sigma of a row is a broadcast shared load
-            const uint32_t base = smem_base + stage * kWgStageBytes + 16384 + cw * 4096 + (lane & 3) * 4;
+            const uint32_t base = rows_smem + kWgHalf + cw * kWgChunk + (lane & 3) * 4;
 #pragma unroll
             for (int rb = 0; rb < 32; rb += 8) {   // 8 rows per batch: all loads first, then the FMAs
               uint32_t v[8];
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
             }
           } else if (head == 2) {
             // warp cw: columns [64 (cw&1), +64) of c1, rows [16 (cw>>1), +16) of the stage
-            const uint32_t base = smem_base + stage * kWgStageBytes + 16384 + (w.b_chunks + (cw & 1)) * 4096 + (lane & 3) * 4;
+            const uint32_t base = rows_smem + kWgHalf + (w.b_chunks + (cw & 1)) * kWgChunk + (lane & 3) * 4;
 #pragma unroll
             for (int rb = 0; rb < 16; rb += 8) {
               const int r0 = (cw >> 1) * 16 + rb;
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
               }
             }
           }
+          }  // r32
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
