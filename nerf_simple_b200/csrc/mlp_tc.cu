@@ -15,10 +15,6 @@
 #include "stream_common.cuh"
 #include "tc_common.cuh"
 
-#ifndef NB_WG_OVH
-#define NB_WG_OVH 48
-#endif
-
 namespace nb200 {
 using namespace tc;
 
@@ -233,7 +229,28 @@ size_t tc_packed_bytes() {
   return h_layout.total_bytes;
 }
 size_t tc_saved_bytes(int64_t M) { return (size_t)ceil_div64(M, kTileM) * kSavedTileBytes; }
-size_t tc_scratch_bytes(int64_t M, int train) { return train ? (size_t)ceil_div64(M, kTileM) * kDeltaTileBytes : 0; }
+// padded staging of the three weight gradients whose rows are not 16-byte multiples (283, 319, 63
+// columns): wgrad flushes into [rows x 320] / [rows x 64] images with vector reductions, and
+// unpad_add_kernel folds them into the real gradients (the scalar-atomic flush of those three layers
+// was 4x slower and left the CTAs holding them ~80 us behind the rest)
+constexpr int kPadPitchWide = 320, kPadPitchX = 64;
+constexpr size_t kPadC0 = 0, kPadSkip = kPadC0 + 128 * kPadPitchWide, kPadL00 = kPadSkip + 256 * kPadPitchWide,
+                 kPadFloats = kPadL00 + 256 * kPadPitchX;
+size_t tc_scratch_bytes(int64_t M, int train) {
+  return train ? (size_t)ceil_div64(M, kTileM) * kDeltaTileBytes + kPadFloats * sizeof(float) : 0;
+}
+
+// grad[r, c] += pad[r, c] for the three padded images (one thread per padded float4 group)
+__global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ pad, float* __restrict__ gC0,
+                                                        float* __restrict__ gSkip, float* __restrict__ gL00) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float index into the pad buffer
+  if (i >= (int)kPadFloats) return;
+  float* g; int r, c, ncols;
+  if (i < (int)kPadSkip) { r = i / kPadPitchWide; c = i - r * kPadPitchWide; g = gC0; ncols = kHidden + kPosD; }
+  else if (i < (int)kPadL00) { const int j = i - (int)kPadSkip; r = j / kPadPitchWide; c = j - r * kPadPitchWide; g = gSkip; ncols = kHidden + kPosX; }
+  else { const int j = i - (int)kPadL00; r = j / kPadPitchX; c = j - r * kPadPitchX; g = gL00; ncols = kPosX; }
+  if (c < ncols) g[(size_t)r * ncols + c] += pad[i];
+}
 
 int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s) {
   NB_TRY_RC(ensure_layout());
@@ -401,6 +418,8 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   const int64_t T = ceil_div64(M, kTileM);
   const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
   uint8_t* ds = reinterpret_cast<uint8_t*>(scratch);
+  float* pad = reinterpret_cast<float*>(ds + (size_t)T * kDeltaTileBytes);
+  NB_CUDA_CHECK(cudaMemsetAsync(pad, 0, kPadFloats * sizeof(float), s));
   // 1. fused delta chain
   BwdParams bp;
   bp.dbg = 0;
@@ -430,6 +449,11 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     w.n_mma = st >= 10 ? 64 : 256;
     w.dW = G[2 * layer]; w.db = bias ? G[2 * layer + 1] : nullptr;
     w.ldw = ldw; w.col0 = col0; w.ncols = ncols; w.nrows = nrows;
+    if (ldw & 3) {  // unaligned rows: flush the whole (zero-padded) accumulator into the padded image
+      w.dW = pad + (layer == L_C0 ? kPadC0 : (layer == L_SKIP ? kPadSkip : kPadL00));
+      w.ldw = layer == L0_0 ? kPadPitchX : kPadPitchWide;
+      w.ncols = w.n_mma;
+    }
     w.cost = (w.a_chunks + w.b_chunks) * 16;
     w.head = 0; w.x_ptr = nullptr; w.x_tile_bytes = 0; w.x_chunks = 0; w.hW = nullptr; w.hb = nullptr;
   };
@@ -456,13 +480,23 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   item(7, 1, L0_2, kHidden, 0, kHidden, kHidden, true);
   item(8, 0, L0_1, kHidden, 0, kHidden, kHidden, true);
   item(9, 10, L0_0, kPosX, 0, kPosX, kHidden, true);                        // layers_0.0 <- posx
-  // measured: a stage costs a fixed latency share on top of its bytes (items with small stages are
-  // latency-bound in the ring); NB_WG_OVH 'KB-equivalents' per tile balance the CTAs (sweeps: 96 was
-  // best with 32-row stages, 32..64 equivalent with 64-row stages)
-  for (int i = 0; i < n; ++i) wp.items[i].cost += NB_WG_OVH;
+  // Relative time per tile of each item kind, MEASURED per CTA on B200 (global-timer trace of the mixed
+  // kernel; bytes alone mis-predict it because small stages are latency-bound in the ring and the head
+  // items add CUDA-core work before a stage is released): plain 256x256 item = 100.
+  for (int i = 0; i < n; ++i) {
+    WItem& w = wp.items[i];
+    const int chunks = w.a_chunks + w.b_chunks + w.x_chunks;
+    int c = chunks == 8 ? 100 : (chunks == 6 ? 85 : (w.db ? 85 : 77));
+    if (w.head == 1) c = 124;
+    if (w.head == 2) c = 83;
+    w.cost = c;
+  }
+  { const char* e = getenv("NB200_WG_ONLY"); if (e) { const int k = atoi(e); if (k >= 0 && k < n) { wp.items[0] = wp.items[k]; n = 1; } } }  // developer probe: time one item alone
   wp.num_items = n;
   mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");
+  unpad_add_kernel<<<((int)kPadFloats + 255) / 256, 256, 0, s>>>(pad, G[2 * L_C0], G[2 * L_SKIP], G[2 * L0_0]);
+  NB_LAUNCH_CHECK("unpad_add_kernel");
   return NB200_OK;
 }
 

@@ -346,6 +346,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+#ifdef NB_WG_TRACE
+  if (threadIdx.x == 0) printf("WGTRACE %d %d %lld %d %lld %llu\n", (int)blockIdx.x, i0, (long long)t0, i1, (long long)t1, (unsigned long long)global_timer_ns());
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
