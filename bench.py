@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 FOV = 0.6911112070083618
 FLOP_FWD = 1186816            # per sample, SURVEY 8d
 FLOP_TRAIN = 3489024
+# algorithmic HBM bytes per sample of the bf16 backward: delta chain reads 4,352 B of ReLU-mask sources + 16 B of d_out and
+# writes 4,864 B of deltas; wgrad reads those deltas, the 5,120 B of saved activations and c1 (256 B) once more
+BWD_BYTES = (4352 + 16 + 4864) + (4864 + 5120 + 256 + 16)
 METRIC = "rays/sec (64 samples/ray) render"
 
 
@@ -333,7 +336,7 @@ def train_arm(args, rank, local_rank, world):
     t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        loss = tr.step()
+        loss = tr.step(time_parts=True)
     e1.record()
     sync_all()
     t_end = time.perf_counter()
@@ -351,6 +354,8 @@ def train_arm(args, rank, local_rank, world):
         lv = tr.step(sync_loss=True)
     sync_all()
     e2e = world * B * args.steps / (time.perf_counter() - t0)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in tr.part_events]))
+    bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in tr.part_events]))
     if rank == 0:
         pk = load_peaks()
         M = B * N
@@ -369,6 +374,16 @@ def train_arm(args, rank, local_rank, world):
                 "roofline": {"kernel": "whole step (fwd+dgrad+wgrad chain kernels dominate)", "bound": "tensor",
                              "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                              "peak_burst": pk["burst"], "flop_per_step": FLOP_TRAIN * M, "traffic": None},
+                # the backward (delta chain + wgrad) is HBM-bound: saved bf16 activations and deltas are the traffic
+                "roofline_backward": {"kernel": "chain_kernel<DgradEpi> + mlp_wgrad_tc_kernel", "bound": "hbm",
+                                      "achieved": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                      "frac": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": bwd_ms,
+                                      "bytes_per_sample": BWD_BYTES,
+                                      "traffic": 5330000000 if (B, N) == (4096, 64) else None,
+                                      "traffic_source": "dram bytes of one dgrad + one wgrad launch, profiles/r1_train_kernels_ncu.txt"},
+                "roofline_forward": {"kernel": "chain_kernel<FwdEpi<save>>", "bound": "tensor", "achieved": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12,
+                                     "peak": pk["sustained"], "unit": "TFLOP/s", "frac": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12 / pk["sustained"],
+                                     "kernel_ms": fwd_ms},
                 "clocks": clocks, "final_loss": float(lv)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,17 +1,19 @@
 """Device-resident drivers of the hot path: what bench.py and the multi-GPU entry points call.
 
-`FrameRenderer` renders whole novel views (the loop of utils/rendering.py:139-151).  Coarse-only
-frames with N in {32, 64, 128} are ONE kernel launch: rays from the camera, Philox jitter, the
-tcgen05 MLP chain and the compositing all happen inside chain_kernel<FwdEpi<render>>, so neither
-rays, sample depths nor per-sample (r,g,b,sigma) touch HBM.  Other shapes (and `fused=False`) use
-the four separate kernels: ray generation, sampler, fused MLP, compositing.  `shard_range` / `render_sharded` split the rays
+`FrameRenderer` renders whole novel views (the loop of utils/rendering.py:139-151) with four kernels
+per frame: ray generation, Philox sampler, fused posenc+MLP, compositing.  With `fused=True` (or
+config.set_fused_render(True)) a coarse-only frame with N in {32, 64, 128} is ONE launch: rays from
+the camera, jitter, the tcgen05 MLP chain and the compositing all happen inside
+chain_kernel<FwdEpi<render>>, so neither rays, sample depths nor per-sample (r,g,b,sigma) touch
+HBM -- measured 2 % slower on B200 (the chain kernel is bound by its epilogue warps, not by HBM),
+hence not the default.  `shard_range` / `render_sharded` split the rays
 of a frame across ranks with one final gather.
 """
 from __future__ import annotations
 
 import torch
 
-from . import _lib, ops
+from . import _lib, config, ops
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -22,11 +24,12 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class FrameRenderer:
-    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None, net_fine=None, Nf=0, fused=True):
+    def __init__(self, net, H, W, f, N=64, tn=2.0, tf=6.0, seed=1, precision=None, net_fine=None, Nf=0, fused=None):
         self.net, self.H, self.W, self.f, self.N = net, int(H), int(W), float(f), int(N)
         self.net_fine, self.Nf = net_fine, int(Nf)   # hierarchical extension: N coarse + Nf fine samples
         self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
         self.precision = precision
+        fused = config.get_fused_render() if fused is None else fused
         self.fused = bool(fused) and net_fine is None and ops.fused_render_supported(net, N, precision)
         self.device = next(net.parameters()).device
         self._offset = 0

@@ -38,9 +38,10 @@ def volume_render(nerf_outs, ts, dirs):
 
 
 def _render_chunk(chunk, net, N):
-    """(rgb, disparity) of one no-grad chunk: the single fused kernel when the shape allows it (bf16,
-    N in {32,64,128}), else render_nerf's three kernels.  Same sampler semantics as render_nerf."""
-    if not ops.fused_render_supported(net, N):
+    """(rgb, disparity) of one no-grad chunk: render_nerf's three kernels, or -- with
+    config.set_fused_render(True) and a supported shape (bf16, N in {32,64,128}) -- the single fused
+    kernel.  Same sampler semantics as render_nerf either way."""
+    if not (config.get_fused_render() and ops.fused_render_supported(net, N)):
         rgb, depth, _, _, _ = render_nerf(chunk, net, N=N)
         return rgb, depth
     if config.get_sampler() == "reference":
@@ -94,7 +95,7 @@ def render_poses(net, poses, cam_params, batch_size, savepath=''):
             rgbs, depths = [], []
             for s in range(0, n, batch_size):
                 cnt = min(batch_size, n - s)
-                if ops.fused_render_supported(net, 128) and config.get_sampler() == "philox":
+                if config.get_fused_render() and ops.fused_render_supported(net, 128) and config.get_sampler() == "philox":
                     rgb, depth, _ = ops.render_fused(net, 128, poses=pose_t, H=H, W=W, f=f, ray_begin=idx * n + s, n_rays=cnt)
                 else:
                     rays = ops.generate_rays(pose_t, H, W, f, ray_begin=idx * n + s, n_rays=cnt)

@@ -42,8 +42,11 @@ def allreduce_mean_(flat_grad, world_size, group=None):
     the global-batch mean of train.py:52).  Works with NCCL (GPU) and gloo (CPU tests)."""
     if world_size > 1:
         import torch.distributed as dist
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-        flat_grad.mul_(1.0 / world_size)
+        if flat_grad.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG, group=group)      # one collective, no scaling kernel
+        else:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            flat_grad.mul_(1.0 / world_size)
     return flat_grad
 
 
@@ -86,9 +89,12 @@ class Trainer:
         self._sel_offset = 0
         self._offset = 0
         self.launches = 0
+        self.part_events = []
         self.last_loss = None
 
-    def step(self, sync_loss=False):
+    def step(self, sync_loss=False, time_parts=False):
+        """One training step.  time_parts=True records CUDA events around the MLP forward and the MLP backward
+        (delta chain + wgrad) in self.part_events for bench.py's roofline."""
         lib = _lib.load()
         dev, B, N, M = self.device, self.B, self.N, self.B * self.N
         st = _lib.stream_ptr(dev)
@@ -102,9 +108,14 @@ class Trainer:
         self._offset += (M + 3) // 4
         packed = self.net._packed.get(self.params, self.precision)
         pa = _lib.ptr_array(self.params)
+        if time_parts:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         _lib.check(lib.nb200_mlp_forward(self.precision, _lib.IN_RAYS, _lib.ptr(rays), _lib.ptr(ts), M, N, pa,
                                          _lib.ptr(packed), _lib.ptr(self._out), _lib.ptr(self._saved), None, 0, st),
                    "nb200_mlp_forward")
+        if time_parts:
+            ev[1].record()
         _lib.check(lib.nb200_composite_forward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, B, N,
                                                _lib.ptr(self._rgb), _lib.ptr(self._disp), _lib.ptr(self._acc),
                                                None, None, st), "nb200_composite_forward")
@@ -116,10 +127,15 @@ class Trainer:
                                                 None, None, None, None, B, N, _lib.ptr(self._dout), st),
                    "nb200_composite_backward")
         self.flat_grad.zero_()
+        if time_parts:
+            ev[2].record()
         _lib.check(lib.nb200_mlp_backward(self.precision, _lib.IN_RAYS, _lib.ptr(rays), _lib.ptr(ts), M, N, pa,
                                           _lib.ptr(packed), _lib.ptr(self._dout), _lib.ptr(self._saved),
                                           _lib.ptr_array(self.grads), _lib.ptr(self._scratch),
                                           self._scratch.numel(), st), "nb200_mlp_backward")
+        if time_parts:
+            ev[3].record()
+            self.part_events.append(ev)
         allreduce_mean_(self.flat_grad, self.world_size)
         self.t += 1
         _lib.check(lib.nb200_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
@@ -127,7 +143,7 @@ class Trainer:
                                        self.betas[1], self.eps, st), "nb200_adam_step")
         self._bump_versions()
         self.lr *= self.lr_decay
-        self.launches += 12 if self.precision == _lib.BF16 else 64   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), adam (+ memset)
+        self.launches += 13 if self.precision == _lib.BF16 else 64   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), unpad, adam (+ 2 memsets)
         self.last_loss = loss
         return float(loss) if sync_loss else loss.clone()
 
