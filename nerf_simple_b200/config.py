@@ -16,6 +16,10 @@ _state = {
     # B200: the MLP kernel is bound by its epilogue warps / the power cap, and the fused kernel adds the sampler
     # and compositing work to exactly those warps); True = one kernel per chunk (no per-sample HBM traffic)
     "fused_render": os.environ.get("NERF_B200_FUSED_RENDER", "0") == "1",
+    # RayGenerator.select: "reference" = CPU randperm over the whole ray table like utils/dataload.py:151
+    # (328 ms per step at 4 M rays); "device" = Philox indices with replacement + gather on the GPU,
+    # rays returned on the device, only the ids (8 B/ray) come back to the host for train.py:49
+    "select": os.environ.get("NERF_B200_SELECT", "reference"),
     "max_samples_per_call": int(os.environ.get("NERF_B200_MAX_SAMPLES", str(1 << 22))),
 }
 
@@ -56,3 +60,13 @@ def set_fused_render(on: bool):
 
 def get_fused_render() -> bool:
     return _state["fused_render"]
+
+
+def set_select(mode: str):
+    if mode not in ("reference", "device"):
+        raise ValueError("select must be 'reference' or 'device'")
+    _state["select"] = mode
+
+
+def get_select() -> str:
+    return _state["select"]

@@ -15,7 +15,7 @@ import re
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, config, ops
 
 
 def _natural_key(path):
@@ -99,8 +99,29 @@ class RayGenerator:
     def select(self, mode='train', N=4096):
         """N random rays of a split and their row ids (utils/dataload.py:141-153)."""
         table = self.rays_dataset[mode]
+        if config.get_select() == "device":
+            return self._select_device(mode, N)
         ray_ids = torch.randperm(table.size(0))[:N]
         return table[ray_ids, :], ray_ids
+
+    def _select_device(self, mode, N):
+        """the same call, without the CPU randperm over the whole table.  Indices are
+        drawn on the device (uniform WITH replacement, Philox), the rays are gathered there and returned
+        as a CUDA tensor (train.py:51's `.cuda()` is then a no-op); the ids come back as the CPU int64
+        tensor train.py:49 indexes the image table with."""
+        lib = _lib.load()
+        if not hasattr(self, "_dev_tables"):
+            self._dev_tables, self._sel_offset = {}, 0
+        if mode not in self._dev_tables:
+            self._dev_tables[mode] = self.rays_dataset[mode].cuda().float().contiguous()
+        table = self._dev_tables[mode]
+        rays = torch.empty((N, 6), dtype=torch.float32, device=table.device)
+        ids = torch.empty((N,), dtype=torch.int64, device=table.device)
+        _lib.check(lib.nb200_select_rays(_lib.ptr(table), None, table.shape[0], config._state["seed"] ^ 0x5E1EC7,
+                                         self._sel_offset, N, _lib.ptr(rays), None, _lib.ptr(ids),
+                                         _lib.stream_ptr(table.device)), "nb200_select_rays")
+        self._sel_offset += N
+        return rays, ids.cpu()
 
     def select_imgs(self, mode='train', N=4096, im_idxs=[0, 1, 2]):
         """N random rays restricted to the given images (utils/dataload.py:155-179)."""

@@ -34,6 +34,17 @@ def test_ray_generator_matches_reference_layout(dataset):
     assert rays.shape == (50, 6) and torch.equal(rays, rg.rays_dataset["train"][ids])
     rays, ids = rg.select_imgs("train", N=40, im_idxs=[1])
     assert rays.shape == (40, 6) and ids.min() >= 64 and ids.max() < 128
+    # opt-in device-side selection: same call, rays on the device, ids on the host
+    from nerf_simple_b200 import config
+    config.set_select("device")
+    try:
+        rays, ids = rg.select("train", N=50)
+        assert rays.is_cuda and not ids.is_cuda and ids.dtype == torch.int64 and rays.shape == (50, 6)
+        assert torch.equal(rays.cpu(), rg.rays_dataset["train"][ids]) and int(ids.min()) >= 0 and int(ids.max()) < 3 * 64
+        _, ids2 = rg.select("train", N=50)
+        assert not torch.equal(ids, ids2)                      # the Philox offset advances from call to call
+    finally:
+        config.set_select("reference")
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
