@@ -35,6 +35,7 @@ class FrameRenderer:
         self._offset = 0
         self.launches = 0          # kernels of libnerf_b200 launched so far
         self.mlp_events = []       # optional (start, stop) CUDA events around the MLP kernel
+        self._copy_stream, self._last_copy = None, None
 
     def render_rays(self, poses_dev, ray_begin, n_rays, time_mlp=False):
         """rgb [n,3] clipped to [0,1] and disparity [n] for rays [ray_begin, ray_begin+n) of the
@@ -85,14 +86,38 @@ class FrameRenderer:
         rgb, disp = self.render_rays(poses_dev, idx * n, n, time_mlp)
         return rgb.view(self.H, self.W, 3), disp.view(self.H, self.W)
 
-    def render_frame_host(self, pose_cpu_pinned, out_rgb_pinned, out_disp_pinned):
-        """End-to-end call with HOST buffers: pose (pinned, [4,4]) in, frame out (pinned)."""
+    def render_frame_host(self, pose_cpu_pinned, out_rgb_pinned, out_disp_pinned, wait=True):
+        """End-to-end call with HOST buffers: pose (pinned, [4,4]) in, frame out (pinned).
+        wait=False returns a CUDA event instead of blocking: the device->host copy of this frame then
+        runs on a side stream under the next frame's kernels (the caller synchronises the event -- or
+        calls `finish()` -- before reading the buffers and must not reuse them for another frame earlier)."""
         pose = pose_cpu_pinned.to(self.device, non_blocking=True).view(1, 4, 4)
         rgb, disp = self.render_frame(pose, 0)
-        out_rgb_pinned.copy_(rgb, non_blocking=True)
-        out_disp_pinned.copy_(disp, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return out_rgb_pinned, out_disp_pinned
+        main = torch.cuda.current_stream(self.device)
+        if wait:
+            out_rgb_pinned.copy_(rgb, non_blocking=True)
+            out_disp_pinned.copy_(disp, non_blocking=True)
+            main.synchronize()
+            return out_rgb_pinned, out_disp_pinned
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        rendered = torch.cuda.Event()
+        rendered.record(main)
+        self._copy_stream.wait_event(rendered)
+        with torch.cuda.stream(self._copy_stream):
+            out_rgb_pinned.copy_(rgb, non_blocking=True)
+            out_disp_pinned.copy_(disp, non_blocking=True)
+            rgb.record_stream(self._copy_stream)
+            disp.record_stream(self._copy_stream)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        self._last_copy = done
+        return done
+
+    def finish(self):
+        """Block until every frame handed to render_frame_host(wait=False) is on the host."""
+        if self._last_copy is not None:
+            self._last_copy.synchronize()
 
 
 def gather_shards(local, n_items, rank, world, group=None):
