@@ -161,5 +161,5 @@ def test_select_rays_and_mse_kernels():
     d_rgb, loss = torch.empty(B, 3, device="cuda"), torch.zeros((), device="cuda")
     rc = lib.nb200_mse_loss_grad(_lib.ptr(rgb.detach()), _lib.ptr(gt), B, _lib.ptr(d_rgb), _lib.ptr(loss), _lib.stream_ptr())
     assert rc == 0
-    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * max(1.0, float(loss_ref))
+    assert abs(float(loss) - loss_ref.item()) <= 1e-6 * max(1.0, loss_ref.item())
     assert float((d_rgb - rgb.grad).abs().max()) <= 1e-9 + 1e-6 * float(rgb.grad.abs().max())
