@@ -99,6 +99,9 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     const bool slot_leader = (threadIdx.x & 255) == 0;  // issues this slot's bulk stores (training kernels)
     for (int64_t k = slot; k < my_pt; k += 2) {
       c.tile = 2 * (cid + k * C) + rank;
+      // the delta chain walks the tiles in REVERSE: the forward pass wrote the saved activations of the last
+      // tiles last, so they are the ones still in L2 when the backward starts
+      if (Epi::kReverseTiles) c.tile = 2 * (PT - 1 - (cid + k * C)) + rank;
       if (Epi::kBulkStore) {  // the previous tile's last tile image must have left shared memory
         if (slot_leader) tma_bulk_store_wait_read();
         slot_barrier(slot);
@@ -439,6 +442,7 @@ struct FwdEpi {
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
   static constexpr int kNumLayers = kNumMmaLayers;
+  static constexpr bool kReverseTiles = false;
   struct State {
     float v[6];
     float sigma;
@@ -548,6 +552,7 @@ struct DgradEpi {
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = true;
   static constexpr int kNumLayers = 9;  // bl = 1..9
+  static constexpr bool kReverseTiles = true;
   struct State { float4 g; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
 

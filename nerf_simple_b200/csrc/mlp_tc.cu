@@ -228,7 +228,11 @@ size_t tc_packed_bytes() {
   if (!h_layout_ready) build_layout();  // layout is host-computable without a device
   return h_layout.total_bytes;
 }
-size_t tc_saved_bytes(int64_t M) { return (size_t)ceil_div64(M, kTileM) * kSavedTileBytes; }
+// Training tensors are laid out for an EVEN number of 128-sample tiles: the chain kernels work on pair-tiles
+// (one tile per CTA of a cluster), so with an odd tile count the second CTA of the last pair still writes a
+// (zero-gradient) tile image, which must not alias tile 0 of the next tensor.
+static int64_t train_tiles(int64_t M) { return (ceil_div64(M, kTileM) + 1) & ~(int64_t)1; }
+size_t tc_saved_bytes(int64_t M) { return (size_t)train_tiles(M) * kSavedTileBytes; }
 // padded staging of the three weight gradients whose rows are not 16-byte multiples (283, 319, 63
 // columns): wgrad flushes into [rows x 320] / [rows x 64] images with vector reductions, and
 // unpad_add_kernel folds them into the real gradients (the scalar-atomic flush of those three layers
@@ -237,7 +241,7 @@ constexpr int kPadPitchWide = 320, kPadPitchX = 64;
 constexpr size_t kPadC0 = 0, kPadSkip = kPadC0 + 128 * kPadPitchWide, kPadL00 = kPadSkip + 256 * kPadPitchWide,
                  kPadFloats = kPadL00 + 256 * kPadPitchX;
 size_t tc_scratch_bytes(int64_t M, int train) {
-  return train ? (size_t)ceil_div64(M, kTileM) * kDeltaTileBytes + kPadFloats * sizeof(float) : 0;
+  return train ? (size_t)train_tiles(M) * kDeltaTileBytes + kPadFloats * sizeof(float) : 0;
 }
 
 // grad[r, c] += pad[r, c] for the three padded images (one thread per padded float4 group)
@@ -340,7 +344,7 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
                                        (int)kCSmemLaunch));
     attr_set = true;
   }
-  const int64_t T = ceil_div64(M, kTileM);
+  const int64_t T = saved ? train_tiles(M) : ceil_div64(M, kTileM);
   NB_TRY_RC(upload_consts(packed, s));
   const TmapPair* tm = nullptr;
   NB_TRY_RC(get_tmaps(packed, &tm));
@@ -415,7 +419,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
     attr_set = true;
   }
-  const int64_t T = ceil_div64(M, kTileM);
+  const int64_t T = train_tiles(M);
   const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
   uint8_t* ds = reinterpret_cast<uint8_t*>(scratch);
   float* pad = reinterpret_cast<float*>(ds + (size_t)T * kDeltaTileBytes);
