@@ -163,3 +163,48 @@ def test_select_rays_and_mse_kernels():
     assert rc == 0
     assert abs(float(loss) - loss_ref.item()) <= 1e-6 * max(1.0, loss_ref.item())
     assert float((d_rgb - rgb.grad).abs().max()) <= 1e-9 + 1e-6 * float(rgb.grad.abs().max())
+
+
+def test_bf16_vs_fp32_trained_render_psnr():
+    """North-star acceptance for the bf16 mode on a TRAINED net: the same weights rendered in bf16 and in fp32
+    give images whose PSNR against the ground truth differs by <= 0.1 dB, and training in bf16 tracks training
+    in fp32 (same initial weights, same ray batches, same jitter)."""
+    from nerf_simple_b200 import config, ops
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.rendering import render_nerf
+    from nerf_simple_b200.xyz import poses_to_render
+    poses = torch.stack(poses_to_render(4, -30, 6)).cuda()
+    H = W = 24
+    rays = ops.generate_rays(poses, H, W, 33.3)
+    gt = torch.sigmoid(rays[:, 3:6] * 3)                      # a smooth, learnable colour field
+    finals, nets = {}, {}
+    for prec in ("fp32", "bf16"):
+        config.set_precision(prec)
+        config.set_sampler("philox", seed=5)                   # same device jitter stream for both runs
+        torch.manual_seed(0)
+        net = Nerf().cuda()
+        opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        losses = []
+        for _ in range(150):
+            ids = torch.randint(0, rays.shape[0], (1024,), device="cuda", generator=g)
+            opt.zero_grad()
+            rgb = render_nerf(rays[ids], net, 32)[0]
+            loss = torch.nn.functional.mse_loss(rgb, gt[ids])
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        finals[prec], nets[prec] = float(np.mean(losses[-20:])), net
+    assert finals["fp32"] < 0.02                                                    # it did train
+    assert abs(finals["bf16"] - finals["fp32"]) <= 0.1 * finals["fp32"]            # bf16 training tracks fp32
+    # one trained net, rendered in both precisions with the same jitter: PSNR delta <= 0.1 dB
+    psnr = {}
+    with torch.no_grad():
+        for prec in ("fp32", "bf16"):
+            config.set_precision(prec)
+            config.set_sampler("philox", seed=9)
+            img = render_nerf(rays[:H * W], nets["fp32"], 64)[0].clamp(0, 1)
+            psnr[prec] = float(-10 * torch.log10(torch.mean((img - gt[:H * W]) ** 2)))
+    config.set_precision("bf16")
+    config.set_sampler("reference")
+    assert abs(psnr["bf16"] - psnr["fp32"]) <= 0.1, psnr
