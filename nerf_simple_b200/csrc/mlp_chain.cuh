@@ -547,6 +547,9 @@ struct FwdEpi {
 };
 
 // ======================================================================= backward (dgrad)
+#ifndef NB_DG_L2HINT
+#define NB_DG_L2HINT 3   // bit 0: mask prefetch evict_last, bit 1: delta stores evict_first (511 -> 495 us)
+#endif
 struct DgradEpi {
   using Params = BwdParams;
   static constexpr bool kHasDbg = false;
@@ -562,7 +565,11 @@ struct DgradEpi {
     if ((threadIdx.x & 255) != 0) return;
     const int bl_next = l + 2;  // layer l+1 has bl = l+2 and masks with tensor 9 - bl
     if (bl_next >= 2 && bl_next <= 9)
+#if NB_DG_L2HINT & 1
+      tma_prefetch_l2_hint(p.saved + saved_tensor_off(9 - bl_next, p.num_tiles) + (size_t)c.tile * 65536, 65536, l2_policy_evict_last());
+#else
       tma_prefetch_l2(p.saved + saved_tensor_off(9 - bl_next, p.num_tiles) + (size_t)c.tile * 65536, 65536);
+#endif
     if (l == 6) {  // c1 tile of this slot's NEXT 128-row tile (begin_tile masks delta_c1 with it)
       const int64_t nt = c.tile + 4 * (int64_t)num_clusters_x();
       if (nt < p.num_tiles) tma_prefetch_l2(p.saved + saved_tensor_off(9, p.num_tiles) + (size_t)nt * 32768, 32768);
@@ -598,8 +605,14 @@ struct DgradEpi {
   // one thread per slot: delta tile image shared -> global (read back by wgrad)
   __device__ static void store_tile(const Params& p, const TileCtx& c, int l) {
     const int64_t T = p.num_tiles;
+#if NB_DG_L2HINT & 2
+    const uint64_t pol = l2_policy_evict_first();
+    if (l == -1) tma_bulk_s2g_hint(p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768, c.a_img, 32768, pol);   // delta_c1
+    else tma_bulk_s2g_hint(p.dscr + delta_tensor_off(l + 1, T) + (size_t)c.tile * 65536, c.a_img, 65536, pol);
+#else
     if (l == -1) tma_bulk_s2g(p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768, c.a_img, 32768);   // delta_c1
     else tma_bulk_s2g(p.dscr + delta_tensor_off(l + 1, T) + (size_t)c.tile * 65536, c.a_img, 65536);
+#endif
   }
 
   __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
