@@ -548,7 +548,8 @@ struct FwdEpi {
 
 // ======================================================================= backward (dgrad)
 #ifndef NB_DG_L2HINT
-#define NB_DG_L2HINT 3   // bit 0: mask prefetch evict_last, bit 1: delta stores evict_first (511 -> 495 us)
+#define NB_DG_L2HINT 2   // bit 1: delta stores evict_first (511 -> 501 us).  bit 0 (mask prefetch evict_last, -6 us more) is off:
+                          // the evict_last lines outlive the kernel and made the first render after training 2x slower
 #endif
 struct DgradEpi {
   using Params = BwdParams;
