@@ -19,15 +19,16 @@ _PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16}
 
 def flat_views(flat, shapes):
     """Views of a flat fp32 buffer for tensors of `shapes`, each starting on a 16-byte boundary (the
-    wgrad kernel flushes aligned rows with vector reductions)."""
-    views, off = [], 0
+    wgrad kernel flushes aligned rows with vector reductions).  One split + one view per tensor."""
+    sizes, padded = [], []
     for shp in shapes:
         n = 1
         for d in shp:
             n *= d
-        views.append(flat[off:off + n].view(shp))
-        off += (n + 3) // 4 * 4
-    return views
+        sizes.append(n)
+        padded.append((n + 3) // 4 * 4)
+    chunks = flat.split(padded) if sum(padded) == flat.numel() else flat[:sum(padded)].split(padded)
+    return [(c if n == p else c[:n]).view(shp) for c, n, p, shp in zip(chunks, sizes, padded, shapes)]
 
 
 def flat_size(shapes):
