@@ -175,6 +175,26 @@ int nb200_select_rays(const float* rays_table, const float* gt_table, int64_t n_
 int nb200_mse_loss_grad(const float* rgb, const float* gt, int64_t B, float* d_rgb, float* loss,
                         nb200_stream_t stream);
 
+/* Device-resident step state for CUDA-graph capture of a whole training step (the loop body of
+ * train.py:47-57 replayed without host involvement).  `state` is NB200_TRAIN_STATE_BYTES of device
+ * memory holding the Philox positions of the ray selection and of the sampler, Adam's step count and
+ * the learning rate; the *_state calls read what their plain counterparts take as host arguments
+ * (offset / step / lr), and nb200_train_state_advance moves it on at the end of a step
+ * (select_offset += select_inc, sample_offset += sample_inc, step += 1, lr *= lr_decay: train.py:56-57).
+ * nb200_train_state_init is a one-time, synchronising set-up call. */
+#define NB200_TRAIN_STATE_BYTES 32
+int nb200_train_state_init(void* state, uint64_t select_offset, uint64_t sample_offset, int64_t step, float lr,
+                           nb200_stream_t stream);
+int nb200_train_state_advance(void* state, uint64_t select_inc, uint64_t sample_inc, float lr_decay,
+                              nb200_stream_t stream);
+int nb200_select_rays_state(const float* rays_table, const float* gt_table, int64_t n_table, uint64_t seed,
+                            const void* state, int64_t B, float* rays, float* gt, int64_t* ids,
+                            nb200_stream_t stream);
+int nb200_stratified_ts_state(uint64_t seed, const void* state, int64_t B, int N, float tn, float tf, float* ts,
+                              nb200_stream_t stream);   /* Philox mode, N % 4 == 0 */
+int nb200_adam_step_state(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const void* state, float beta1, float beta2, float eps, nb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

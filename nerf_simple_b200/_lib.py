@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("NERF_B200_LIB", os.path.join(_HERE, "libnerf_b200.so"
 OK = 0
 FP32, BF16 = 0, 1
 IN_POINTS, IN_RAYS = 0, 1
+TRAIN_STATE_BYTES = 32     # NB200_TRAIN_STATE_BYTES
 
 # every symbol include/nerf_b200.h declares: name -> (restype, argtypes)
 _p, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -42,6 +43,11 @@ SYMBOLS = {
     "nb200_render_camera": (_i, [_i, _p, _i, _i, _i, _f, _i64, _i64, _u64, _u64, _i, _f, _f, _p, _p, _p, _p, _p]),
     "nb200_select_rays": (_i, [_p, _p, _i64, _u64, _u64, _i64, _p, _p, _p, _p]),
     "nb200_mse_loss_grad": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "nb200_train_state_init": (_i, [_p, _u64, _u64, _i64, _f, _p]),
+    "nb200_train_state_advance": (_i, [_p, _u64, _u64, _f, _p]),
+    "nb200_select_rays_state": (_i, [_p, _p, _i64, _u64, _p, _i64, _p, _p, _p, _p]),
+    "nb200_stratified_ts_state": (_i, [_u64, _p, _i64, _i, _f, _f, _p, _p]),
+    "nb200_adam_step_state": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _p]),
     "nb200_sample_pdf_merge": (_i, [_p, _p, _p, _i, _u64, _u64, _i64, _i, _i, _p, _p]),
 }
 

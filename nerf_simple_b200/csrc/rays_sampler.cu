@@ -79,9 +79,11 @@ __global__ void __launch_bounds__(256) stratified_ts_kernel(const float* __restr
 template <bool kHasU>
 __global__ void __launch_bounds__(256) stratified_ts_quad_kernel(const float* __restrict__ u, uint64_t seed,
                                                                  uint64_t offset, int64_t nquads, int N, int64_t stride,
-                                                                 float tn, float tf, float* __restrict__ ts) {
+                                                                 float tn, float tf, float* __restrict__ ts,
+                                                                 const uint64_t* __restrict__ offset_dev) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= stride) return;
+  if (offset_dev) offset += *offset_dev;   // device-resident stream position (CUDA-graph replays)
   const float step = __fdiv_rn(tf - tn, (float)N);
   const float bin = __fsub_rn(tbin(1, N, tn, tf, step), tbin(0, N, tn, tf, step));
   const float scale = kHasU ? bin : bin * 5.9604644775390625e-08f;
@@ -141,9 +143,10 @@ __global__ void __launch_bounds__(256) select_rays_kernel(const float* __restric
                                                           const float* __restrict__ gt_table, int64_t n_table,
                                                           uint64_t seed, uint64_t offset, int64_t B,
                                                           float* __restrict__ rays, float* __restrict__ gt,
-                                                          int64_t* __restrict__ ids) {
+                                                          int64_t* __restrict__ ids, const uint64_t* __restrict__ offset_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
+  if (offset_dev) offset += *offset_dev;
   const uint4 x = philox4x32_10(offset + (uint64_t)i, seed);
   // 64 random bits -> [0, n_table): high word of the 64x64 product (bias < n_table * 2^-64)
   const uint64_t r64 = ((uint64_t)x.y << 32) | x.x;
@@ -182,6 +185,42 @@ __global__ void __launch_bounds__(1024) mse_loss_grad_kernel(const float* __rest
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     if (threadIdx.x == 0 && loss != nullptr) *loss = v / (float)n;
   }
+}
+
+// ------------------------------------------------------------------ device-resident step state
+// What changes from one training step to the next lives on the device, so that a whole step can be
+// captured once in a CUDA graph and replayed: Philox stream positions, Adam's step count, the lr.
+struct TrainState {
+  uint64_t select_offset;   // Philox counter of the ray selection
+  uint64_t sample_offset;   // Philox counter of the stratified sampler (quads)
+  int64_t step;             // optimizer steps taken so far
+  float lr;                 // current learning rate
+  float pad;
+};
+static_assert(sizeof(TrainState) == NB200_TRAIN_STATE_BYTES, "train state layout");
+
+__global__ void __launch_bounds__(256) adam_flat_state_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                              float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                              const TrainState* __restrict__ st, float beta1, float beta2, float eps) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float t = (float)(st->step + 1);
+  const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  const float step_size = st->lr / bc1;
+  for (int64_t i = i4; i < n && i < i4 + 4; ++i) {
+    const float gi = g[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+__global__ void train_state_advance_kernel(TrainState* st, uint64_t select_inc, uint64_t sample_inc, float lr_decay) {
+  st->select_offset += select_inc;
+  st->sample_offset += sample_inc;
+  st->step += 1;
+  st->lr *= lr_decay;       // train.py:56-57
 }
 
 }  // namespace nb200
@@ -230,9 +269,9 @@ int nb200_stratified_ts(const float* u, uint64_t seed, uint64_t offset, int64_t 
     const int64_t threads = (int64_t)grid * 256;
     const int64_t stride = threads - threads % (N >> 2);
     if (u)
-      stratified_ts_quad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts);
+      stratified_ts_quad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts, nullptr);
     else
-      stratified_ts_quad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts);
+      stratified_ts_quad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total >> 2, N, stride, tn, tf, ts, nullptr);
   } else {
     stratified_ts_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, seed, offset, total, N, tn, tf, ts, aligned);
   }
@@ -248,7 +287,7 @@ int nb200_select_rays(const float* rays_table, const float* gt_table, int64_t n_
   if (!rays_table || !rays || (gt_table && !gt)) return NB200_ERR_ARG;
   if ((((uintptr_t)rays_table | (uintptr_t)rays) & 7) != 0) return NB200_ERR_ARG;
   select_rays_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, as_stream(stream)>>>(rays_table, gt_table, n_table, seed, offset,
-                                                                                B, rays, gt, ids);
+                                                                                B, rays, gt, ids, nullptr);
   NB_LAUNCH_CHECK("select_rays_kernel");
   return NB200_OK;
 }
@@ -258,6 +297,67 @@ int nb200_mse_loss_grad(const float* rgb, const float* gt, int64_t B, float* d_r
   if (B <= 0 || !rgb || !gt || !d_rgb) return NB200_ERR_ARG;
   mse_loss_grad_kernel<<<1, 1024, 0, as_stream(stream)>>>(rgb, gt, B * 3, d_rgb, loss);
   NB_LAUNCH_CHECK("mse_loss_grad_kernel");
+  return NB200_OK;
+}
+
+// ---- variants that read the per-step quantities from a device-resident nb200 train state (CUDA graphs)
+int nb200_train_state_init(void* state, uint64_t select_offset, uint64_t sample_offset, int64_t step, float lr,
+                           nb200_stream_t stream) {
+  using namespace nb200;
+  if (!state) return NB200_ERR_ARG;
+  TrainState h = {select_offset, sample_offset, step, lr, 0.f};
+  // the source must outlive the async copy: pass by value through a kernel-free, stream-ordered memset + small memcpys
+  NB_CUDA_CHECK(cudaMemcpyAsync(state, &h, sizeof(h), cudaMemcpyHostToDevice, as_stream(stream)));
+  NB_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));   // one-time set-up call
+  return NB200_OK;
+}
+
+int nb200_train_state_advance(void* state, uint64_t select_inc, uint64_t sample_inc, float lr_decay, nb200_stream_t stream) {
+  using namespace nb200;
+  if (!state) return NB200_ERR_ARG;
+  train_state_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<TrainState*>(state), select_inc, sample_inc, lr_decay);
+  NB_LAUNCH_CHECK("train_state_advance_kernel");
+  return NB200_OK;
+}
+
+int nb200_select_rays_state(const float* rays_table, const float* gt_table, int64_t n_table, uint64_t seed, const void* state,
+                            int64_t B, float* rays, float* gt, int64_t* ids, nb200_stream_t stream) {
+  using namespace nb200;
+  if (B < 0 || n_table <= 0 || !state) return NB200_ERR_ARG;
+  if (B == 0) return NB200_OK;
+  if (!rays_table || !rays || (gt_table && !gt)) return NB200_ERR_ARG;
+  if ((((uintptr_t)rays_table | (uintptr_t)rays) & 7) != 0) return NB200_ERR_ARG;
+  select_rays_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, as_stream(stream)>>>(
+      rays_table, gt_table, n_table, seed, 0, B, rays, gt, ids, &reinterpret_cast<const TrainState*>(state)->select_offset);
+  NB_LAUNCH_CHECK("select_rays_kernel");
+  return NB200_OK;
+}
+
+int nb200_stratified_ts_state(uint64_t seed, const void* state, int64_t B, int N, float tn, float tf, float* ts,
+                              nb200_stream_t stream) {
+  using namespace nb200;
+  if (B < 0 || N < 4 || (N & 3) || N > 1024 || !state) return NB200_ERR_ARG;   // quad kernel only
+  const int64_t total = B * (int64_t)N;
+  if (total == 0) return NB200_OK;
+  if (!ts || ((uintptr_t)ts & 15)) return NB200_ERR_ARG;
+  const int64_t blocks = ceil_div64(ceil_div64(total, 4), 256);
+  const int grid = (int)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
+  const int64_t threads = (int64_t)grid * 256;
+  const int64_t stride = threads - threads % (N >> 2);
+  stratified_ts_quad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
+      nullptr, seed, 0, total >> 2, N, stride, tn, tf, ts, &reinterpret_cast<const TrainState*>(state)->sample_offset);
+  NB_LAUNCH_CHECK("stratified_ts_quad_kernel");
+  return NB200_OK;
+}
+
+int nb200_adam_step_state(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const void* state,
+                          float beta1, float beta2, float eps, nb200_stream_t stream) {
+  using namespace nb200;
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || !state) return NB200_ERR_ARG;
+  if (n == 0) return NB200_OK;
+  adam_flat_state_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, as_stream(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, reinterpret_cast<const TrainState*>(state), beta1, beta2, eps);
+  NB_LAUNCH_CHECK("adam_flat_state_kernel");
   return NB200_OK;
 }
 

@@ -6,7 +6,9 @@ the ray table and the ground-truth colours live on the device, a step is
     select -> Philox jitter -> fused MLP forward (saving bf16 tiles) -> compositing forward ->
     MSE gradient -> compositing backward -> delta chain -> wgrad -> [all-reduce] -> Adam
 and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
-needs exactly one NCCL all-reduce of 595,844 floats per step.
+needs exactly one NCCL all-reduce of 595,844 floats per step.  Everything that varies
+from step to step lives in a 32-byte device-resident state, so after two eager warm-up steps the
+whole step is captured in a CUDA graph and replayed (use_graph=True, single-GPU runs).
 """
 from __future__ import annotations
 
@@ -52,7 +54,7 @@ def allreduce_mean_(flat_grad, world_size, group=None):
 
 class Trainer:
     def __init__(self, net, rays_table, gt_table, N=64, batch_size=4096, lr=5e-4, lr_decay=1.0,
-                 tn=2.0, tf=6.0, seed=1, precision="bf16", world_size=1):
+                 tn=2.0, tf=6.0, seed=1, precision="bf16", world_size=1, use_graph=True):
         self.net, self.N, self.B = net, int(N), int(batch_size)
         self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
         self.precision = {"fp32": _lib.FP32, "bf16": _lib.BF16}[precision]
@@ -86,28 +88,49 @@ class Trainer:
         self._gt = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
         self._drgb = torch.empty((self.B, 3), dtype=torch.float32, device=self.device)
         self._loss = torch.zeros((), dtype=torch.float32, device=self.device)
-        self._sel_offset = 0
+        self._ts = torch.empty((self.B, self.N), dtype=torch.float32, device=self.device)
         self._offset = 0
+        # device-resident step state (Philox positions, Adam step, lr) + stable pointer arrays: a step is a fixed
+        # sequence of launches that a CUDA graph can replay
+        self._state = torch.zeros(_lib.TRAIN_STATE_BYTES, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.nb200_train_state_init(_lib.ptr(self._state), 0, 0, 0, self.lr, _lib.stream_ptr(self.device)),
+                   "nb200_train_state_init")
+        self._param_ptrs = _lib.ptr_array(self.params)
+        self._grad_ptrs = _lib.ptr_array(self.grads)
+        self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
+                            if self.precision == _lib.BF16 else None)
+        # single-GPU only: capturing the NCCL all-reduce of the data-parallel step hung on this stack (torch 2.11, NCCL
+        # 2.28, two ranks), so multi-rank steps are launched eagerly (the collective costs 26 us of a 1.4 ms step)
+        self.use_graph = (bool(use_graph) and world_size == 1 and self.precision == _lib.BF16
+                          and self.N % 4 == 0 and self.N <= 1024)
+        self._graph, self.graph_error = None, None
         self.launches = 0
         self.part_events = []
         self.last_loss = None
 
-    def step(self, sync_loss=False, time_parts=False):
-        """One training step.  time_parts=True records CUDA events around the MLP forward and the MLP backward
-        (delta chain + wgrad) in self.part_events for bench.py's roofline."""
+    def _enqueue_step(self, time_parts=False):
+        """Enqueue one training step on the current stream.  Everything that changes from step to step (Philox
+        positions, Adam's step count, the learning rate) is read from the device-resident train state, so
+        the same sequence of launches can be captured once in a CUDA graph and replayed."""
         lib = _lib.load()
         dev, B, N, M = self.device, self.B, self.N, self.B * self.N
         st = _lib.stream_ptr(dev)
+        state = _lib.ptr(self._state)
         # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
-        rays, gt = self._rays, self._gt
-        _lib.check(lib.nb200_select_rays(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
-                                         self.seed ^ 0x5E1EC7, self._sel_offset, B, _lib.ptr(rays), _lib.ptr(gt), None, st),
-                   "nb200_select_rays")
-        self._sel_offset += B
-        ts = ops.stratified_ts(B, N, self.tn, self.tf, device=dev, seed=self.seed, offset=self._offset)
-        self._offset += (M + 3) // 4
-        packed = self.net._packed.get(self.params, self.precision)
-        pa = _lib.ptr_array(self.params)
+        rays, gt, ts = self._rays, self._gt, self._ts
+        _lib.check(lib.nb200_select_rays_state(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
+                                               self.seed ^ 0x5E1EC7, state, B, _lib.ptr(rays), _lib.ptr(gt), None, st),
+                   "nb200_select_rays_state")
+        if N % 4 == 0 and N <= 1024:
+            _lib.check(lib.nb200_stratified_ts_state(self.seed, state, B, N, self.tn, self.tf, _lib.ptr(ts), st),
+                       "nb200_stratified_ts_state")
+        else:   # ragged N: host-side stream position (not graph-replayable; use_graph is off for such N)
+            _lib.check(lib.nb200_stratified_ts(None, self.seed, self._offset, B, N, self.tn, self.tf, _lib.ptr(ts), st),
+                       "nb200_stratified_ts")
+        pa = self._param_ptrs
+        packed = self._packed_buf
+        if self.precision == _lib.BF16:   # the optimizer changed the fp32 masters: refresh the bf16 operand images
+            _lib.check(lib.nb200_pack_weights(self.precision, pa, _lib.ptr(packed), st), "nb200_pack_weights")
         if time_parts:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -120,10 +143,9 @@ class Trainer:
                                                _lib.ptr(self._rgb), _lib.ptr(self._disp), _lib.ptr(self._acc),
                                                None, None, st), "nb200_composite_forward")
         # MSELoss over B*3 and its gradient (train.py:42,52)
-        d_rgb, loss = self._drgb, self._loss
-        _lib.check(lib.nb200_mse_loss_grad(_lib.ptr(self._rgb), _lib.ptr(gt), B, _lib.ptr(d_rgb), _lib.ptr(loss), st),
+        _lib.check(lib.nb200_mse_loss_grad(_lib.ptr(self._rgb), _lib.ptr(gt), B, _lib.ptr(self._drgb), _lib.ptr(self._loss), st),
                    "nb200_mse_loss_grad")
-        _lib.check(lib.nb200_composite_backward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, _lib.ptr(d_rgb),
+        _lib.check(lib.nb200_composite_backward(_lib.ptr(self._out), _lib.ptr(ts), _lib.ptr(rays), 1, _lib.ptr(self._drgb),
                                                 None, None, None, None, B, N, _lib.ptr(self._dout), st),
                    "nb200_composite_backward")
         self.flat_grad.zero_()
@@ -131,21 +153,50 @@ class Trainer:
             ev[2].record()
         _lib.check(lib.nb200_mlp_backward(self.precision, _lib.IN_RAYS, _lib.ptr(rays), _lib.ptr(ts), M, N, pa,
                                           _lib.ptr(packed), _lib.ptr(self._dout), _lib.ptr(self._saved),
-                                          _lib.ptr_array(self.grads), _lib.ptr(self._scratch),
-                                          self._scratch.numel(), st), "nb200_mlp_backward")
+                                          self._grad_ptrs, _lib.ptr(self._scratch), self._scratch.numel(), st),
+                   "nb200_mlp_backward")
         if time_parts:
             ev[3].record()
             self.part_events.append(ev)
         allreduce_mean_(self.flat_grad, self.world_size)
+        _lib.check(lib.nb200_adam_step_state(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                             _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state, self.betas[0],
+                                             self.betas[1], self.eps, st), "nb200_adam_step_state")
+        _lib.check(lib.nb200_train_state_advance(state, B, (M + 3) // 4, self.lr_decay, st), "nb200_train_state_advance")
+
+    def _capture(self):
+        """Capture one step in a CUDA graph (after eager warm-up steps have set kernel attributes, cached the
+        tensor maps and initialised NCCL).  Falls back to eager launches if the capture fails."""
+        try:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step()
+            self._graph = g
+        except Exception as e:   # e.g. a collective that cannot be captured on this setup
+            self._graph, self.use_graph = None, False
+            self.graph_error = repr(e)
+            torch.cuda.synchronize(self.device)
+
+    def step(self, sync_loss=False, time_parts=False):
+        """One training step.  time_parts=True (eager launches only) records CUDA events around the MLP forward
+        and the MLP backward (delta chain + wgrad) in self.part_events for bench.py's roofline."""
+        if self.use_graph and not time_parts:
+            if self._graph is None and self.t >= 2:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._enqueue_step()
+        else:
+            self._enqueue_step(time_parts)
         self.t += 1
-        _lib.check(lib.nb200_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
-                                       _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), self.t, self.lr, self.betas[0],
-                                       self.betas[1], self.eps, st), "nb200_adam_step")
-        self._bump_versions()
+        self._offset += (self.B * self.N + 3) // 4
         self.lr *= self.lr_decay
-        self.launches += 13 if self.precision == _lib.BF16 else 64   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), unpad, adam (+ 2 memsets)
-        self.last_loss = loss
-        return float(loss) if sync_loss else loss.clone()
+        self._bump_versions()
+        self.launches += 14 if self.precision == _lib.BF16 else 65   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), unpad, adam, state (+ 2 memsets)
+        self.last_loss = self._loss
+        return float(self._loss) if sync_loss else self._loss.clone()
 
     def _bump_versions(self):
         # the optimizer updated the flat buffer, not the 24 views: invalidate the packed-weight cache
