@@ -427,8 +427,8 @@ def train_arm(args, rank, local_rank, world):
                                       "achieved": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                       "frac": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": bwd_ms,
                                       "bytes_per_sample": BWD_BYTES,
-                                      "traffic": 5478000000 if (B, N) == (4096, 64) else None,
-                                      "traffic_source": "dram bytes of one dgrad + one wgrad launch, profiles/r1b_train_kernels_ncu.txt (2.616 GB delta chain + 2.862 GB wgrad)"},
+                                      "traffic": 5383000000 if (B, N) == (4096, 64) else None,
+                                      "traffic_source": "dram bytes of one dgrad + one wgrad launch, profiles/r1c_train_kernels_ncu.txt (2.522 GB delta chain + 2.861 GB wgrad)"},
                 "roofline_forward": {"kernel": "chain_kernel<FwdEpi<save>>", "bound": "tensor", "achieved": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12,
                                      "peak": pk["sustained"], "unit": "TFLOP/s", "frac": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12 / pk["sustained"],
                                      "kernel_ms": fwd_ms},
