@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 48, bar_accfull = bar_base + 96,
                  bar_accempty = bar_base + 104, tmem_slot = bar_base + 112;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef NB_WG_TRACE
+  const uint64_t trace_t0 = global_timer_ns();
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
 #ifdef NB_WG_TRACE
-  if (threadIdx.x == 0) printf("WGTRACE %d %d %lld %d %lld %llu\n", (int)blockIdx.x, i0, (long long)t0, i1, (long long)t1, (unsigned long long)global_timer_ns());
+  if (threadIdx.x == 0) printf("WGTRACE %d %d %lld %d %lld %llu %llu\n", (int)blockIdx.x, i0, (long long)t0, i1, (long long)t1, (unsigned long long)global_timer_ns(), (unsigned long long)trace_t0);
 #endif
   if (warp == 1) {
     tc_fence_after();

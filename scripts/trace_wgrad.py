@@ -1,6 +1,7 @@
 """Developer probe: per-CTA end times of mlp_wgrad_tc_kernel.  Build a library with -DNB_WG_TRACE
 (scripts/build_variants.sh mlp_tc.cu trace "-DNB_WG_TRACE"), run this under NERF_B200_LIB=...lib_trace.so and
-grep WGTRACE: block, first item, first tile, last item, last tile, global timer (ns) at exit."""
+grep WGTRACE: block, first item, first tile, last item, last tile, global timer (ns) at exit and at entry.
+Last measured: CTA durations 390-416 us (mean 404) inside a 420 us launch, 2.0-3.1 us per tile by item kind."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nerf_simple_b200 import ops
