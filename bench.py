@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20 frames for render, 500 steps for train)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -454,6 +454,8 @@ def main():
     ap.add_argument("--render-path", default="separate", choices=["separate", "fused"],
                     help="separate: raygen, sampler, fused posenc+MLP, compositing kernels; fused: one kernel per frame")
     args = ap.parse_args()
+    if args.steps is None:      # a train step is ~1.3 ms: enough of them for nvidia-smi to sample the clocks in the timed region
+        args.steps = 500 if (args.workload == "train" and args.impl == "b200") else 20
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
