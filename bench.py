@@ -411,7 +411,8 @@ def train_arm(args, rank, local_rank, world):
                 "config": {"workload": f"configs[2]: training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, "
                                        f"fused compositing backward", "rays_table": "25 views 400x400 (4.0 M rays) on device",
                            "parallelism": f"data-parallel over {world} rank(s), one all-reduce of 595,844 fp32 grads/step",
-                           "launch": "CUDA-graph replay of the whole step" if tr._graph is not None else "eager launches",
+                           "launch": ("eager launches" if tr._graph is None else ("CUDA-graph replay of the whole step" if len(tr._graph) == 1
+                                      else "two CUDA graphs per step around the eagerly launched NCCL all-reduce")),
                            "l2": "saved activations + deltas per step = 2.6 GB (larger than L2)"},
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
                         "api": "Trainer.step(sync_loss=True): loss read back every step"},

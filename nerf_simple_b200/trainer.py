@@ -8,7 +8,8 @@ the ray table and the ground-truth colours live on the device, a step is
 and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
 needs exactly one NCCL all-reduce of 595,844 floats per step.  Everything that varies
 from step to step lives in a 32-byte device-resident state, so after two eager warm-up steps the
-whole step is captured in a CUDA graph and replayed (use_graph=True, single-GPU runs).
+whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks, two graphs
+around the eagerly launched all-reduce).
 """
 from __future__ import annotations
 
@@ -99,16 +100,15 @@ class Trainer:
         self._grad_ptrs = _lib.ptr_array(self.grads)
         self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
                             if self.precision == _lib.BF16 else None)
-        # single-GPU only: capturing the NCCL all-reduce of the data-parallel step hung on this stack (torch 2.11, NCCL
-        # 2.28, two ranks), so multi-rank steps are launched eagerly (the collective costs 26 us of a 1.4 ms step)
-        self.use_graph = (bool(use_graph) and world_size == 1 and self.precision == _lib.BF16
-                          and self.N % 4 == 0 and self.N <= 1024)
+        # (capturing the NCCL all-reduce itself hung on this stack -- torch 2.11, NCCL 2.28, two ranks -- so multi-rank
+        # steps replay two graphs with the collective launched eagerly in between)
+        self.use_graph = bool(use_graph) and self.precision == _lib.BF16 and self.N % 4 == 0 and self.N <= 1024
         self._graph, self.graph_error = None, None
         self.launches = 0
         self.part_events = []
         self.last_loss = None
 
-    def _enqueue_step(self, time_parts=False):
+    def _enqueue_step(self, time_parts=False, part="all"):
         """Enqueue one training step on the current stream.  Everything that changes from step to step (Philox
         positions, Adam's step count, the learning rate) is read from the device-resident train state, so
         the same sequence of launches can be captured once in a CUDA graph and replayed."""
@@ -116,6 +116,8 @@ class Trainer:
         dev, B, N, M = self.device, self.B, self.N, self.B * self.N
         st = _lib.stream_ptr(dev)
         state = _lib.ptr(self._state)
+        if part == "update":
+            return self._enqueue_update(lib, state, st)
         # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
         rays, gt, ts = self._rays, self._gt, self._ts
         _lib.check(lib.nb200_select_rays_state(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
@@ -158,22 +160,38 @@ class Trainer:
         if time_parts:
             ev[3].record()
             self.part_events.append(ev)
+        if part == "grads":      # multi-rank graph mode: the all-reduce is launched eagerly between the two graphs
+            return
         allreduce_mean_(self.flat_grad, self.world_size)
+        self._enqueue_update(lib, state, st)
+
+    def _enqueue_update(self, lib, state, st):
+        B, M = self.B, self.B * self.N
         _lib.check(lib.nb200_adam_step_state(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                              _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state, self.betas[0],
                                              self.betas[1], self.eps, st), "nb200_adam_step_state")
         _lib.check(lib.nb200_train_state_advance(state, B, (M + 3) // 4, self.lr_decay, st), "nb200_train_state_advance")
 
     def _capture(self):
-        """Capture one step in a CUDA graph (after eager warm-up steps have set kernel attributes, cached the
-        tensor maps and initialised NCCL).  Falls back to eager launches if the capture fails."""
+        """Capture one step in CUDA graphs (after eager warm-up steps have set kernel attributes, cached the
+        tensor maps and initialised NCCL).  Single rank: one graph.  Several ranks: one graph up to the local
+        gradients and one for the optimizer update, with the NCCL all-reduce launched eagerly in between
+        (capturing the collective itself hung on this stack).  Falls back to eager launches on failure."""
         try:
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue_step()
-            self._graph = g
-        except Exception as e:   # e.g. a collective that cannot be captured on this setup
+            if self.world_size == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step()
+                self._graph = (g,)
+            else:
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._enqueue_step(part="grads")
+                with torch.cuda.graph(gb):
+                    self._enqueue_step(part="update")
+                self._graph = (ga, gb)
+        except Exception as e:
             self._graph, self.use_graph = None, False
             self.graph_error = repr(e)
             torch.cuda.synchronize(self.device)
@@ -185,7 +203,10 @@ class Trainer:
             if self._graph is None and self.t >= 2:
                 self._capture()
             if self._graph is not None:
-                self._graph.replay()
+                self._graph[0].replay()
+                if len(self._graph) == 2:
+                    allreduce_mean_(self.flat_grad, self.world_size)
+                    self._graph[1].replay()
             else:
                 self._enqueue_step()
         else:
