@@ -73,8 +73,6 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.lr_decay = lr_decay
-        self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(seed)
         lib = _lib.load()
         M = self.B * self.N
         self._out = torch.empty((M, 4), dtype=torch.float32, device=self.device)

@@ -90,3 +90,33 @@ def test_dropin_module_surface():
         sys.path.pop(0)
         for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             del sys.modules[m]
+
+
+def test_flat_views_are_aligned_contiguous_views():
+    """The flat parameter / gradient buffers of the trainer: every tensor is a contiguous view that starts on
+    a 16-byte boundary (vector reductions in the wgrad flush), padding floats included in the size."""
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.ops import NUM_PARAMS, flat_size, flat_views
+    shapes = [tuple(p.shape) for p in Nerf().parameters()]
+    assert sum(int(np.prod(s)) for s in shapes) == NUM_PARAMS == 595844
+    n = flat_size(shapes)
+    flat = torch.arange(n, dtype=torch.float32)
+    views = flat_views(flat, shapes)
+    off = 0
+    for v, shp in zip(views, shapes):
+        assert tuple(v.shape) == shp and v.is_contiguous()
+        assert v.data_ptr() == flat.data_ptr() + 4 * off and off % 4 == 0
+        off += (v.numel() + 3) // 4 * 4
+    assert off == n and n - NUM_PARAMS < 4 * len(shapes)
+
+
+def test_config_switches_validate():
+    from nerf_simple_b200 import config
+    for bad, fn in (("fp16", config.set_precision), ("torch", config.set_sampler), ("gpu", config.set_select)):
+        with pytest.raises(ValueError):
+            fn(bad)
+    assert config.get_precision() in ("bf16", "fp32") and config.get_sampler() in ("reference", "philox")
+    assert config.get_select() == "reference" and config.get_fused_render() is False      # defaults = reference semantics
+    seed, off0 = config.next_philox(10)
+    _, off1 = config.next_philox(1)
+    assert off1 - off0 == 3                                                               # ceil(10 / 4) Philox calls reserved
