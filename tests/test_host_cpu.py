@@ -120,3 +120,20 @@ def test_config_switches_validate():
     seed, off0 = config.next_philox(10)
     _, off1 = config.next_philox(1)
     assert off1 - off0 == 3                                                               # ceil(10 / 4) Philox calls reserved
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm) prints one JSON line with
+    the contract's keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["metric"].startswith("rays/sec") and line["config"]["workload"].startswith("configs[1]")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
