@@ -17,13 +17,9 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 
 
 def import_reference():
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    sys.path.insert(0, REF)
-    import utils.nets as nets            # noqa: E402
-    import utils.rendering as rendering  # noqa: E402
-    import utils.xyz as xyz              # noqa: E402
-    return nets, rendering, xyz
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle.ref_import import import_reference as imp     # .cuda() no-op shim + natsort stand-in
+    return imp(cpu=True, root=REF)
 
 
 def np_(t):
@@ -149,6 +145,67 @@ def main():
         rg[f"{tag}.rays"] = np_(rays_w)
     rg["poses30"] = np_(torch.stack(xyz.poses_to_render(r=4, theta=-30, n_phi=30)))
     np.savez(os.path.join(OUT, "case_raygen.npz"), **rg)
+    # ---- case F: BASELINE configs[2] at full size -- one training step 4096 rays x 64 samples
+    # (train.py:47-54: MSE through rgb only), all 24 gradients.  The jitter is NOT stored: tests redraw it
+    # with torch.manual_seed(21); torch.rand(4096, 64) (the stream render_nerf consumes at :28).
+    rays800, f800, _ = dome_rays(xyz, 800, 800, n_phi=30, pose_idx=7)
+    sel = torch.randperm(rays800.shape[0], generator=g)[:4096]
+    rays_f = rays800[sel].contiguous()
+    gt_f = torch.rand(4096, 3, generator=g)
+    torch.manual_seed(21)
+    net.zero_grad()
+    rgb_f, disp_f, _, acc_f, _ = rendering.render_nerf(rays_f, net, 64)
+    loss_f = torch.nn.MSELoss()(rgb_f, gt_f)
+    loss_f.backward()
+    np.savez(os.path.join(OUT, "case_train_b4096_n64.npz"), rays=np_(rays_f), gt=np_(gt_f), u_seed=np.int64(21),
+             rgb=np_(rgb_f), disp=np_(disp_f), acc=np_(acc_f), loss=np.float32(loss_f.item()),
+             **{"grad." + k: np_(p.grad) for k, p in net.named_parameters()})
+
+    # ---- case G: the reference's own chunk loops (utils/rendering.py:88-113 render_image, :116-153
+    # render_poses), divisible sizes, seeded CPU generator (one torch.rand(chunk,128) per chunk, :102,:145)
+    Hh = Wh = 20
+    fh = Wh / (2 * np.tan(0.6911112070083618 / 2))
+    poses_g = xyz.poses_to_render(4, -30, 4)
+    dirs_g = xyz.rays_single_cam([Hh, Wh, fh])
+    Pg = torch.stack(poses_g)
+    rays_g = torch.cat((Pg[:, :3, 3:].expand(4, 3, Hh * Wh), torch.matmul(Pg[:, :3, :3], dirs_g)), dim=1)
+    rays_g = rays_g.permute(0, 2, 1).reshape(-1, 6).contiguous()
+    gt_imgs = [np.random.default_rng(5 + i).random((Hh, Wh, 3)) for i in range(4)]
+
+    class RG:
+        samples = {"val": [{"img": im} for im in gt_imgs]}
+        rays_dataset = {"val": rays_g}
+    # shift the colour biases so that the image straddles the [0,1] clip of :103 on two channels
+    net_g = nets.Nerf()
+    net_g.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        net_g.color_fc[2].bias.add_(torch.tensor([0.5, 1.07, -0.13]))
+        net_g.sigma_fc[0].bias.add_(0.3)
+    torch.manual_seed(31)
+    with torch.no_grad():
+        img_rgb, img_depth, img_gt = rendering.render_image(net_g, RG, batch_size=100, im_idx=2, im_set="val")
+    # render_poses returns nothing: record the uint8 BGR frames it hands to cv2.VideoWriter (:155-160)
+    import cv2
+    frames = []
+
+    class Recorder:
+        def __init__(self, *a):
+            self.args = a
+        def write(self, fr):
+            frames.append(np.array(fr))
+        def release(self):
+            pass
+    real_writer = cv2.VideoWriter
+    cv2.VideoWriter = Recorder
+    try:
+        torch.manual_seed(32)
+        rendering.render_poses(net_g, poses_g[:2], [Hh, Wh, fh], 80, savepath="")
+    finally:
+        cv2.VideoWriter = real_writer
+    np.savez(os.path.join(OUT, "case_chunk_loops.npz"), cam=np.array([Hh, Wh, fh], np.float64), poses=np_(Pg),
+             rays=np_(rays_g), gt2=gt_imgs[2], bias_shift=np.array([0.5, 1.07, -0.13, 0.3], np.float32),
+             image_seed=np.int64(31), image_rgb=np_(img_rgb), image_depth=np_(img_depth), image_gt=np.asarray(img_gt),
+             poses_seed=np.int64(32), frames_bgr_u8=np.stack(frames))
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

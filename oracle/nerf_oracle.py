@@ -260,10 +260,11 @@ def volume_render_backward(nerf_outs, ts, dirs, d_rgb, d_disp=None, d_alpha=None
 
 
 # ------------------------------------------------------------------------- pipeline
-def render_nerf(rays, P, N, u, tn=2.0, tf=6.0, Lp=10, Ld=4, dtype=np.float32, keep=False):
+def render_nerf(rays, P, N, u, tn=2.0, tf=6.0, Lp=10, Ld=4, dtype=np.float32, keep=False, ts=None):
     """utils/rendering.py:13-45 with the uniform jitter u[B,N] supplied by the caller (the
-    reference draws it from the CPU global generator at :28)."""
-    ts = stratified_ts(u, N, tn, tf)
+    reference draws it from the CPU global generator at :28).  `ts` [B,N] given: use these sample
+    depths instead of lines :25-29 (checks of device-sampled batches, where u never exists on the host)."""
+    ts = stratified_ts(u, N, tn, tf) if ts is None else np.asarray(ts, np.float32)
     q, dn = sample_points(rays, ts, dtype)
     res = mlp_forward(q, P, Lp, Ld, dtype, keep=keep)
     out, saved = res if keep else (res, None)
@@ -274,9 +275,9 @@ def render_nerf(rays, P, N, u, tn=2.0, tf=6.0, Lp=10, Ld=4, dtype=np.float32, ke
     return outs
 
 
-def train_step_grads(rays, P, N, u, gt, dtype=np.float32):
+def train_step_grads(rays, P, N, u, gt, dtype=np.float32, ts=None):
     """train.py:51-54: loss = mean((rgb - gt)^2) over B*3; returns (loss, grads dict, rgb)."""
-    outs, sv = render_nerf(rays, P, N, u, dtype=dtype, keep=True)
+    outs, sv = render_nerf(rays, P, N, u, dtype=dtype, keep=True, ts=ts)
     rgb = outs[0]
     diff = rgb - gt.astype(dtype)
     loss = np.mean(diff * diff)
@@ -326,6 +327,16 @@ def spherical_to_pose(r, theta_deg, phi_deg):
 def poses_to_render(r, theta, n_phi=40):
     """utils/xyz.py:83-91: azimuths linspace(0,360,n_phi) inclusive, fp32 poses."""
     return [spherical_to_pose(r, theta, p).astype(np.float32) for p in np.linspace(0, 360.0, n_phi)]
+
+
+def adam_step(param, grad, m, v, t, lr=5e-4, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam(lr=5e-4) single step (train.py:43,55; no weight decay / amsgrad), t 1-based:
+    m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)."""
+    g = grad.astype(np.float64)
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    denom = np.sqrt(v) / np.sqrt(1 - b2 ** t) + eps
+    return (param.astype(np.float64) - (lr / (1 - b1 ** t)) * m / denom).astype(np.float32), m, v
 
 
 def init_params(seed: int = 0) -> dict:

@@ -142,3 +142,101 @@ def test_sample_pdf_extension_properties():
         assert np.all(np.isin(ts[b], z[b]))
         inside = np.sum((z[b] >= ts[b, 29]) & (z[b] <= ts[b, 35]))
         assert inside >= 0.9 * Nf
+
+
+def _chunk_loop_net(golden_weights):
+    g = load_golden("case_chunk_loops.npz")
+    P = {k: v.copy() for k, v in golden_weights.items()}
+    P["color_fc.2.bias"] = P["color_fc.2.bias"] + g["bias_shift"][:3]
+    P["sigma_fc.0.bias"] = P["sigma_fc.0.bias"] + g["bias_shift"][3]
+    return g, P
+
+
+def test_full_size_train_step(golden_weights):
+    """BASELINE configs[2] at full size (4096 rays x 64 samples): loss, rgb and all 24 gradients of the
+    reference's autograd (train.py:51-54).  The jitter is the CPU stream of utils/rendering.py:28."""
+    import torch
+    g = load_golden("case_train_b4096_n64.npz")
+    torch.manual_seed(int(g["u_seed"]))
+    u = torch.rand(4096, 64).numpy()
+    loss, grads, rgb = O.train_step_grads(g["rays"], golden_weights, 64, u, g["gt"])
+    assert abs(loss - float(g["loss"])) <= 1e-6
+    assert maxabs(rgb, g["rgb"]) <= 5e-6
+    for n in O.PARAM_NAMES:
+        ref = g["grad." + n]
+        scale = max(1e-6, float(np.max(np.abs(ref))))
+        assert maxabs(grads[n], ref) <= 5e-4 * scale + 1e-7, n
+    # the same step with the sample depths handed over directly (how device-sampled batches are checked)
+    loss2, grads2, _ = O.train_step_grads(g["rays"], golden_weights, 64, None, g["gt"], ts=O.stratified_ts(u, 64))
+    assert loss2 == loss and all(np.array_equal(grads[n], grads2[n]) for n in O.PARAM_NAMES)
+
+
+def test_chunk_loops_match_reference(golden_weights):
+    """render_image / render_poses of the reference (utils/rendering.py:88-160): chunked N=128 renders, one
+    torch.rand(chunk,128) per chunk from the seeded CPU generator, clip to [0,1], uint8 BGR video frames."""
+    import torch
+    g, P = _chunk_loop_net(golden_weights)
+    H, W, f = int(g["cam"][0]), int(g["cam"][1]), float(g["cam"][2])
+    rays = g["rays"][2 * H * W:3 * H * W]
+    torch.manual_seed(int(g["image_seed"]))
+    rgbs, disps = [], []
+    for s in range(0, H * W, 100):
+        u = torch.rand(100, 128).numpy()
+        rgb, disp, *_ = O.render_nerf(rays[s:s + 100], P, 128, u)
+        rgbs.append(np.clip(rgb, 0, 1)); disps.append(disp)
+    assert maxabs(np.concatenate(rgbs).reshape(1, H, W, 3), g["image_rgb"]) <= 5e-6
+    assert np.max(np.abs(np.concatenate(disps).reshape(1, H, W, 1) - g["image_depth"]) / g["image_depth"]) <= 2e-5
+    assert np.array_equal(g["image_gt"][0], g["gt2"])
+    # render_poses: rays from the poses (rays_single_cam + R @ dirs), frames as the writer receives them
+    dirs = O.rays_single_cam(H, W, f)
+    assert maxabs(O.world_rays(g["poses"], dirs), g["rays"]) <= 1e-6
+    torch.manual_seed(int(g["poses_seed"]))
+    for idx in range(2):
+        fr = []
+        for s in range(0, H * W, 80):
+            u = torch.rand(80, 128).numpy()
+            fr.append(np.clip(O.render_nerf(g["rays"][idx * H * W + s:idx * H * W + s + 80], P, 128, u)[0], 0, 1))
+        bgr = (np.concatenate(fr).reshape(H, W, 3)[..., ::-1] * 255).astype(np.uint8)       # :158-159
+        assert np.max(np.abs(bgr.astype(int) - g["frames_bgr_u8"][idx].astype(int))) <= 1    # truncation at a .0 boundary
+
+
+def test_adam_restatement_matches_torch():
+    import torch
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(1000).astype(np.float32)
+    ref = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([ref], lr=5e-4)
+    p, m, v = p0.copy(), np.zeros(1000), np.zeros(1000)
+    for t in range(1, 5):
+        gr = (rng.standard_normal(1000) * 0.1 * t).astype(np.float32)
+        ref.grad = torch.from_numpy(gr.copy())
+        opt.step()
+        p, m, v = O.adam_step(p, gr, m, v, t)
+    assert maxabs(p, ref.detach().numpy()) <= 1e-6
+
+
+def test_staged_reference_reproduces_goldens(golden_weights):
+    """When the real reference is available (build container: /root/reference; GPU box: baseline/_ref), run it
+    and compare with the committed fixture -- the oracle is pinned by live execution, not only by files."""
+    import subprocess
+    import sys
+    import os
+    from oracle.ref_import import reference_root, ROOT
+    if reference_root() is None:
+        pytest.skip("no reference checkout staged")
+    code = (
+        "import numpy as np, torch, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from oracle.ref_import import import_reference\n"
+        "nets, rendering, xyz = import_reference(cpu=True)\n"
+        f"g = dict(np.load({os.path.join(ROOT, 'tests', 'golden', 'case_render_b1024_n64.npz')!r}))\n"
+        "torch.manual_seed(0); net = nets.Nerf()\n"
+        "torch.manual_seed(11)\n"
+        "with torch.no_grad(): o = rendering.render_nerf(torch.from_numpy(g['rays'][:256]), net, 64)\n"
+        "print('MAXDIFF', float((o[0] - torch.from_numpy(g['rgb'][:256])).abs().max()))\n")
+    # (render_nerf draws torch.rand(B, N) row-major, so the first 256 rays see the first 256 rows of u only
+    # when B is the same; use the whole batch instead)
+    code = code.replace("g['rays'][:256]", "g['rays']").replace("g['rgb'][:256]", "g['rgb']")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.split("MAXDIFF")[1]) <= 1e-6
