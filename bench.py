@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: rays/sec of the NeRF hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload render|train] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|render|train] [--impl reference]
 
-Default workload = BASELINE.json configs[1]: full 800x800 novel-view render, 64 samples/ray,
-spherical-dome camera path, synthetic lego-shaped scene, seeded random-init weights.  One step =
-one frame per GPU: ray generation -> stratified sampling -> fused posenc+MLP (tcgen05) ->
-compositing, all on the device.  Multi-GPU (torchrun, one rank per GPU): frames of the dome path
-are sharded across ranks (weak scaling) and the rendered pixels are all-gathered (16 B/ray).
+Headline workload = BASELINE.json configs[1]: full 800x800 novel-view render, 64 samples/ray, spherical-dome camera
+path, synthetic lego-shaped scene, seeded random-init weights.  One step = one frame per GPU: ray generation ->
+stratified sampling -> fused posenc+MLP (tcgen05) -> compositing, all on the device.  Under torchrun (one rank per GPU)
+the frames of the dome path are sharded across ranks (weak scaling) and gathered on rank 0.
 
-`--impl reference` times the reference's CPU implementation of the same path (numpy restatement
-in oracle/, all host cores) on a bounded sample of the same workload.
-Prints ONE JSON line on rank 0.
+The same JSON line carries sub-records measured in the same run (`--workload all`, the default):
+  train          configs[2]: training step 4096 rays x 64 samples per GPU, fwd + bwd + Adam (data-parallel for N > 1)
+  train_dp8192   configs[4]: 8192 rays per GPU, data-parallel, one all-reduce of the 595,844 gradients per step
+  sharded_frame  configs[4]: ONE 1600x1600 frame split into ray bands over the ranks + one all_gather (strong scaling)
+  n128           the reference's default 128 samples/ray (configs/lego.yaml:6)
+
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, staged by scripts/stage_reference.sh; its own
+render_nerf, CPU, all host threads) on a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -29,10 +33,8 @@ sys.path.insert(0, ROOT)
 FOV = 0.6911112070083618
 FLOP_FWD = 1186816            # per sample, SURVEY 8d
 FLOP_TRAIN = 3489024
-# algorithmic HBM bytes per sample of the bf16 backward: delta chain reads 4,352 B of ReLU-mask sources + 16 B of d_out and
-# writes 4,864 B of deltas; wgrad reads those deltas, the 5,120 B of saved activations and c1 (256 B) once more
-BWD_BYTES = (4352 + 16 + 4864) + (4864 + 5120 + 256 + 16)
 METRIC = "rays/sec (64 samples/ray) render"
+REF_CHUNK = 16000             # test.py's batch size (configs/lego.yaml:18): the reference arm's bounded sample per step
 
 
 def load_peaks():
@@ -45,8 +47,29 @@ def load_peaks():
         return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_traffic(kernel_key):
+    """DRAM bytes per launch of `kernel_key` from the committed ncu capture summary (profiles/traffic.json, written by
+    scripts/summarize_profiles.py from an `ncu --set full` report); None when no capture of this build exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        e = t.get(kernel_key)
+        return (e["dram_bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def workload_config(H, W, N, world):
+    """The keys that name the workload -- identical in the B200 arm and the reference arm."""
+    return {"workload": f"configs[1]: full {H}x{W} novel-view render, {N} samples/ray, spherical-dome path "
+                        f"(poses_to_render(4,-30,30)), one frame per GPU per step",
+            "H": H, "W": W, "N": N, "rays_per_frame": H * W, "weights": "torch.manual_seed(0); Nerf()",
+            "parallelism": f"frames sharded over {world} rank(s), gathered on rank 0",
+            "l2": f"inputs larger than L2: {H * W * N * 16 / 1e6:.0f} MB of per-sample (r,g,b,sigma) + {H * W * N * 4 / 1e6:.0f} MB of ts per frame"}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled for the whole run; window(t0, t1) summarises a timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -66,20 +89,13 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self, t_begin=None, t_end=None):
-        """Summarise the samples taken inside [t_begin, t_end] (host clock); the sampler is started
-        before the warm-up so that nvidia-smi's own start-up never lands in the timed region."""
+    def window(self, t_begin, t_end):
         if self.proc is None:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if t_begin is not None and not (t_begin <= ts <= t_end):
+        for ts, ln in list(self.lines):
+            if not (t_begin <= ts <= t_end + 0.15):
                 continue
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 7:
@@ -93,277 +109,403 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def close(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
 
 
 # ------------------------------------------------------------------------- reference / CPU arm
-def oracle_render_sample(n_rays, N, chunk, seed=0):
-    """Times the CPU restatement of the reference path on a bounded sample: `n_rays` rays of the
-    800x800 dome view, N samples/ray, `chunk`-ray chunks (configs[0] shape), no_grad render.  The
-    port is the torch-CPU op sequence of the reference (oracle/nerf_oracle_torch.py) with all
-    intra-op threads; ray setup comes from the numpy oracle."""
-    import torch
-    from oracle import nerf_oracle as O        # CPU baseline leg only
-    from oracle import nerf_oracle_torch as OT
-    torch.set_num_threads(os.cpu_count())
-    P = {k: torch.from_numpy(v) for k, v in O.init_params(seed).items()}
-    f = 800 / (2 * np.tan(FOV / 2))
+def dome_rays_numpy(H, W, pose_idx, begin, count):
+    from oracle import nerf_oracle as O            # CPU arm only: ray set-up of the sample
+    f = W / (2 * np.tan(FOV / 2))
     poses = np.stack(O.poses_to_render(4, -30, 30))
-    dirs = O.rays_single_cam(800, 800, f)
-    start = 800 * 400 + 100
-    rays = torch.from_numpy(O.world_rays(poses[1:2], dirs[:, start:start + n_rays]))
-    torch.manual_seed(1)
-
-    def run():
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            for s in range(0, n_rays, chunk):
-                r = rays[s:s + chunk]
-                rgb, *_ = OT.render_nerf(r, P, N, torch.rand(r.shape[0], N))
-                rgb.clamp_(0, 1)
-        return time.perf_counter() - t0
-    return run
+    dirs = O.rays_single_cam(H, W, f)
+    return O.world_rays(poses[pose_idx:pose_idx + 1], dirs[:, begin:begin + count])
 
 
 def reference_arm(args, rank):
+    """The reference's own CPU implementation of the path: baseline/_ref (or /root/reference in the build container)
+    imported unmodified, `.cuda()` no-op shim, fp32, all host threads.  Falls back to the torch-CPU port in oracle/
+    only when no reference checkout is available, and says which."""
     if rank != 0:
         return
-    n_rays, N, chunk = 2048, 64, 1024
-    run = oracle_render_sample(n_rays, N, chunk)
+    import torch
+    from oracle.ref_import import import_reference, reference_root
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    H = W = args.res
+    N = args.samples
+    n_rays = min(REF_CHUNK, H * W)
+    root = reference_root()
+    rays = torch.from_numpy(dome_rays_numpy(H, W, 1, (H // 2) * W, n_rays))
+    if root is not None:
+        nets, rendering, xyz = import_reference(cpu=True, root=root)
+        torch.manual_seed(0)
+        net = nets.Nerf()
+        kind, what = "reference", f"unmodified reference utils/rendering.py:render_nerf imported from {os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}"
+
+        def render(r, n):
+            rgb, *_ = rendering.render_nerf(r, net, n)
+            return rgb
+    else:
+        from oracle import nerf_oracle as O
+        from oracle import nerf_oracle_torch as OT
+        P = {k: torch.from_numpy(v) for k, v in O.init_params(0).items()}
+        kind, what = "port", "torch-CPU port of the reference ops (oracle/nerf_oracle_torch.py): no reference checkout staged"
+        net = None
+
+        def render(r, n):
+            return OT.render_nerf(r, P, n, torch.rand(r.shape[0], n))[0]
+    torch.manual_seed(1)
+
+    def step():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            render(rays, N).clamp_(0, 1)          # one test.py-sized chunk of the frame (utils/rendering.py:143-146)
+        return time.perf_counter() - t0
     for _ in range(args.warmup):
-        run()
-    times = [run() for _ in range(args.steps)]
+        step()
+    times = [step() for _ in range(args.steps)]
     ms = 1e3 * float(np.mean(times))
     val = n_rays / (ms * 1e-3)
-    cores = os.cpu_count()
-    sample = f"{n_rays} rays of the 800x800 dome view x {N} samples, {chunk}-ray chunks, torch-CPU fp32 port of the reference ops, {cores} intra-op threads"
+    sample = (f"{n_rays} rays (one {REF_CHUNK}-ray chunk, test.py's batch size) of the same {H}x{W} dome view x {N} samples per step; "
+              f"{what}; fp32, {cores} intra-op threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1] 800x800 novel-view render, 64 samples/ray (bounded sample per step)",
-                       "H": 800, "W": 800, "N": N},
-            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(H, W, N, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_extras and kind == "reference":
+        # BASELINE configs[0], the reference's own CPU-runnable case: whole 100x100 frame in 1024-ray chunks, and one
+        # training step 1024 rays x 64 (train.py:47-55), best of 2 after a warm-up
+        r100 = torch.from_numpy(dome_rays_numpy(100, 100, 1, 0, 10000))
+
+        def frame100():
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                for s in range(0, 10000, 1024):
+                    render(r100[s:s + 1024], 64).clamp_(0, 1)
+            return time.perf_counter() - t0
+        frame100()
+        line["config0_frame_100x100x64"] = {"value": 10000 / min(frame100(), frame100()), "unit": "rays/s", "chunk": 1024}
+        opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+        crit = torch.nn.MSELoss()
+        gt = torch.rand(1024, 3)
+
+        def train_step():
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            rgb, *_ = rendering.render_nerf(r100[:1024], net, 64)
+            crit(rgb, gt).backward()
+            opt.step()
+            return time.perf_counter() - t0
+        train_step()
+        line["config0_train_step_1024x64"] = {"value": 1024 / min(train_step(), train_step()), "unit": "rays/s"}
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess(args):
+    """Run the reference arm in a process of its own (its `.cuda()` no-op shim is process-wide) on a short schedule."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4", "--warmup", "1",
+           "--res", str(args.res), "--samples", str(args.samples)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        cb = ref["cpu_baseline"]
+        for k in ("config0_frame_100x100x64", "config0_train_step_1024x64"):
+            if k in ref:
+                cb[k] = ref[k]
+        return cb
+    except Exception as e:      # the baseline is reported context, never a reason to lose the GPU measurement
+        return {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
+
+
+def reference_gpu_eager(H, W, N, dev):
+    """Context only: the UNMODIFIED reference run eagerly on this same B200 (its ATen/cuBLAS path, fp32 matmuls as
+    torch >= 1.12 defaults), one whole frame in test.py-sized chunks.  None when baseline/_ref is not staged."""
+    import torch
+    from oracle.ref_import import import_reference, reference_root
+    root = reference_root()
+    if root is None:
+        return None
+    nets, rendering, xyz = import_reference(cpu=False, root=root)
+    torch.manual_seed(0)
+    net = nets.Nerf().cuda()
+    rays = torch.from_numpy(dome_rays_numpy(H, W, 1, 0, H * W))
+    with torch.no_grad():
+        for s in (0, REF_CHUNK):                                   # warm-up chunks (cuBLAS handles, allocator)
+            rendering.render_nerf(rays[s:s + REF_CHUNK].cuda(), net, N)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for s in range(0, H * W - REF_CHUNK + 1, REF_CHUNK):       # utils/rendering.py:143-146
+            rgb, *_ = rendering.render_nerf(rays[s:s + REF_CHUNK].cuda(), net, N)
+            torch.clip(rgb, torch.tensor(0.).cuda(), torch.tensor(1.).cuda())
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    n = (H * W // REF_CHUNK) * REF_CHUNK
+    return {"value": n / dt, "unit": "rays/s", "what": f"unmodified reference render_nerf on cuda:0, eager ATen/cuBLAS fp32, {n} rays "
+            f"of one {H}x{W} frame in {REF_CHUNK}-ray chunks, N={N}, host ray table + per-chunk H2D like utils/rendering.py:139-151"}
+
+
 # ------------------------------------------------------------------------------------ B200 arm
-def b200_arm(args, rank, local_rank, world):
+class Ctx:
+    pass
+
+
+def setup(args, local_rank, world):
     import torch
     import torch.distributed as dist
     from nerf_simple_b200 import _lib, config
+    _lib.load()                               # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local_rank)
+    c = Ctx()
+    c.dev = torch.device("cuda", local_rank)
+    c.world, c.rank = world, int(os.environ.get("RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=c.dev)
+    config.set_precision(args.precision)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(c.dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=c.dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    c.sync_all, c.max_over_ranks = sync_all, max_over_ranks
+    c.sampler = ClockSampler(local_rank) if c.rank == 0 else None
+    return c
+
+
+def bench_render(args, c, H, W, N, steps, warmup, fine=0, fused=False, e2e=True, api=True):
+    """Frames-per-GPU render (weak scaling): value, MLP-kernel time, e2e through host buffers."""
+    import torch
+    import torch.distributed as dist
     from nerf_simple_b200.engine import FrameRenderer
     from nerf_simple_b200.nets import Nerf
     from nerf_simple_b200.xyz import poses_to_render
-
-    _lib.load()                               # fail loudly if the CUDA library is missing
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    config.set_precision(args.precision)
-    H = W = args.res
-    N = args.samples
+    dev, world, rank = c.dev, c.world, c.rank
     f = W / (2 * np.tan(FOV / 2))
     torch.manual_seed(0)
     net = Nerf().to(dev)                      # random-init weights of the reference architecture
     poses = torch.stack(poses_to_render(4, -30, 30)).to(dev)
     n_poses = poses.shape[0]
-    net_fine = Nerf().to(dev) if args.fine > 0 else None     # --fine 128: hierarchical extension (config 4)
-    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=args.fine,
-                         fused=(args.render_path == "fused"))
+    net_fine = Nerf().to(dev) if fine > 0 else None     # --fine 128: hierarchical extension (configs[3])
+    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=fine, fused=fused)
     n_rays = H * W
-    gather_buf = [torch.empty((n_rays, 4), device=dev) for _ in range(world)] if world > 1 else None
+    # the frames of the dome path are gathered on rank 0 (16 B/ray), asynchronously: the collective of frame i runs under
+    # the kernels of frame i+1 (two send buffers); no rank ever receives frames it does not need
+    send = [torch.empty((n_rays, 4), device=dev) for _ in range(2)] if world > 1 else None
+    recv = [[torch.empty((n_rays, 4), device=dev) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else None
+    pending = [None, None]
 
     def step(i, timed):
         idx = (i * world + rank) % n_poses    # frames of the dome path sharded over ranks
         rgb, disp = rend.render_frame(poses, idx, time_mlp=timed)
-        if world > 1:                         # final gather of the pixels (16 B/ray)
-            dist.all_gather(gather_buf, torch.cat([rgb.view(-1, 3), disp.view(-1, 1)], dim=1))
+        if world > 1:
+            b = i & 1
+            if pending[b] is not None:
+                pending[b].wait()
+            send[b][:, :3].copy_(rgb.view(-1, 3)); send[b][:, 3].copy_(disp.view(-1))
+            pending[b] = dist.gather(send[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
         return rgb
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i, False)
-    sync_all()
+    drain()
+    c.sync_all()
     launches0 = rend.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i, True)
+    drain()
     e1.record()
-    sync_all()
+    c.sync_all()
     t_end = time.perf_counter()
-    clocks = sampler.stop(t_begin, t_end) if sampler else None
-    ms_total = e0.elapsed_time(e1)
-    gpu_launches = rend.launches - launches0
-    mlp_ms = float(np.mean([a.elapsed_time(b) for a, b in rend.mlp_events]))
+    ms_step = c.max_over_ranks(e0.elapsed_time(e1)) / steps
+    r = {"value": world * n_rays / (ms_step * 1e-3), "ms_per_step": ms_step, "gpu_launches": rend.launches - launches0,
+         "mlp_ms": float(np.mean([a.elapsed_time(b) for a, b in rend.mlp_events])), "t_window": (t_begin, t_end), "fused": rend.fused}
     rend.mlp_events.clear()
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = world * n_rays / (ms_step * 1e-3)
-
-    # ---- end-to-end through the public host-buffer API: pose on the host in, frame on the host out
-    pose_host = [poses[i].cpu().pin_memory() for i in range(n_poses)]
-    out_rgb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-    out_disp = torch.empty((H, W), dtype=torch.float32).pin_memory()
-    for i in range(2):
-        rend.render_frame_host(pose_host[i], out_rgb, out_disp)
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        rend.render_frame_host(pose_host[(i * world + rank) % n_poses], out_rgb, out_disp)
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * n_rays * args.steps / float(t.item())
-    finite = bool(torch.isfinite(out_rgb).all())
-
-    # ---- the reference's own host driver, unchanged call: render_image(net, rg, batch_size=16000, ...)
-    # (utils/rendering.py:88-113; test.py batch size): CPU ray table in, per-chunk H2D, CPU frame out.
-    api_val = None
-    if world == 1 and args.fine == 0:
-        from nerf_simple_b200.rendering import render_image
+    if e2e:
+        # ---- end to end through the public host-buffer API: pose on the host in, frame on the host out
+        pose_host = [poses[i].cpu().pin_memory() for i in range(n_poses)]
+        out_rgb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+        out_disp = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            rend.render_frame_host(pose_host[i], out_rgb, out_disp)
+        c.sync_all()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            rend.render_frame_host(pose_host[(i * world + rank) % n_poses], out_rgb, out_disp)
+        c.sync_all()
+        r["e2e"] = world * n_rays * steps / c.max_over_ranks(time.perf_counter() - t0)
+        r["finite"] = bool(torch.isfinite(out_rgb).all())
+        # ---- the video path of render_poses: uint8 BGR frame out (3 B/pixel)
+        out_u8 = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        rend.render_frame_u8_host(pose_host[0], out_u8)
+        c.sync_all()
+        t0 = time.perf_counter()
+        reps = max(3, steps // 2)
+        for i in range(reps):
+            rend.render_frame_u8_host(pose_host[(i * world + rank) % n_poses], out_u8)
+        c.sync_all()
+        r["e2e_u8"] = world * n_rays * reps / c.max_over_ranks(time.perf_counter() - t0)
+    if api and world == 1 and fine == 0:
+        # ---- the reference's own host driver, unchanged call: render_image(net, rg, batch_size=16000, ...)
+        # (utils/rendering.py:88-113; test.py batch size): CPU ray table in, per-chunk H2D, CPU frame out.
+        from nerf_simple_b200 import config
         from nerf_simple_b200 import ops as _ops
+        from nerf_simple_b200.rendering import render_image
 
         class _RG:
             samples = {"test": [{"img": np.zeros((H, W, 3))}]}
             rays_dataset = {"test": _ops.generate_rays(poses[1:2], H, W, f).cpu()}
         config.set_sampler("philox")
-        render_image(net, _RG, batch_size=16000, im_idx=0, im_set="test", N=N)
+        render_image(net, _RG, batch_size=REF_CHUNK, im_idx=0, im_set="test", N=N)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        reps = max(2, args.steps // 4)
+        reps = max(2, steps // 4)
         for _ in range(reps):
-            render_image(net, _RG, batch_size=16000, im_idx=0, im_set="test", N=N)
+            render_image(net, _RG, batch_size=REF_CHUNK, im_idx=0, im_set="test", N=N)
         torch.cuda.synchronize(dev)
-        api_val = reps * n_rays / (time.perf_counter() - t0)
-
-    if rank == 0:
-        pk = load_peaks()
-        M = n_rays * N
-        achieved = FLOP_FWD * M / (mlp_ms * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "samples_per_sec": value * N,
-            "config": {"workload": f"configs[1]: full {H}x{W} novel-view render, {N} samples/ray, spherical-dome path "
-                                   f"(poses_to_render(4,-30,30)), one frame per GPU per step",
-                       "H": H, "W": W, "N": N, "N_fine": args.fine, "rays_per_step_per_gpu": n_rays, "weights": "torch.manual_seed(0); Nerf()",
-                       "sampler": "device Philox seed 1", "parallelism": f"frames sharded over {world} rank(s) + all_gather of pixels",
-                       "render_path": ("one kernel per frame (camera -> sampler -> MLP -> compositing in chain_kernel<FwdEpi<render>>)"
-                                       if rend.fused else "4 kernels per frame: raygen, Philox sampler, fused posenc+MLP, compositing"),
-                       "l2": ("fused path: nothing but the 3.4 MB weight image (L2-resident by design) is re-read between steps; 10 MB of pixels written per frame"
-                              if rend.fused else f"inputs larger than L2: {n_rays * N * 16 / 1e6:.0f} MB of per-sample (r,g,b,sigma) + {n_rays * N * 4 / 1e6:.0f} MB of ts per frame")},
-            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 64,
-                    "d2h_bytes_per_step": n_rays * 16, "api": "FrameRenderer.render_frame_host(pose_pinned) -> pinned frame"},
-            "e2e_render_image_api": {"value": api_val, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24,
-                                     "d2h_bytes_per_step": n_rays * 16,
-                                     "api": "render_image(net, rg, batch_size=16000): CPU ray table, 40 chunks, CPU frame"},
-            "gpu_launches": gpu_launches,
-            "roofline": {"kernel": ("chain_kernel<FwdEpi<render>> (camera rays + sampler + posenc + MLP + compositing, tcgen05 cta_group::2)" if rend.fused
-                                     else "chain_kernel<FwdEpi<false>> (fused posenc+MLP, tcgen05 cta_group::2)"), "bound": "tensor", "achieved": achieved, "peak": pk["sustained"],
-                         "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "peak_burst": pk["burst"],
-                         "frac_burst": achieved / pk["burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                         "kernel_ms": mlp_ms, "flop_per_launch": FLOP_FWD * M,
-                         "traffic": 792493568 if (H, W, N) == (800, 800, 64) and not rend.fused else None,
-                         "traffic_source": "dram__bytes_read+write.sum of one launch, profiles/r1_fwd_chain_v2_ncu_raw.csv "
-                                           "(algorithmic: 655 MB out + 164 MB ts + 15 MB rays)"},
-            "clocks": clocks, "outputs_finite": finite,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            n_s, chunk = 4096, 1024
-            run = oracle_render_sample(n_s, N, chunk)
-            run()
-            tt = min(run() for _ in range(3))
-            line["cpu_baseline"] = {"value": n_s / tt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{n_s} rays of the same 800x800 view x {N} samples in {chunk}-ray chunks, "
-                                              f"torch-CPU fp32 port of the reference ops (oracle/), all cores, best of 3"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        r["api"] = reps * n_rays / (time.perf_counter() - t0)
+        config.set_sampler("reference")
+    return r
 
 
-def train_arm(args, rank, local_rank, world):
-    """BASELINE configs[2]: training step, 4096 rays x 64 samples per GPU, fwd+bwd+Adam, data-parallel
+def bench_sharded_frame(args, c, H, W, N, frames, warmup=2):
+    """BASELINE configs[4], render half: ONE HxW frame split into contiguous ray bands over the ranks
+    (utils/rendering.py:139-151 is the loop being sharded) + one all_gather of (rgb, disp) = 16 B/ray.  Strong scaling."""
+    import torch
+    from nerf_simple_b200.engine import FrameRenderer, render_sharded
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.xyz import poses_to_render
+    dev, world, rank = c.dev, c.world, c.rank
+    f = W / (2 * np.tan(FOV / 2))
+    torch.manual_seed(0)
+    net = Nerf().to(dev)
+    poses = torch.stack(poses_to_render(4, -30, 30)).to(dev)
+    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision)
+    for i in range(warmup):
+        render_sharded(rend, poses, i % 30, rank, world)
+    c.sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record()
+    for i in range(frames):
+        rgb, disp = render_sharded(rend, poses, i % 30, rank, world)
+    e1.record()
+    c.sync_all()
+    t_end = time.perf_counter()
+    ms = c.max_over_ranks(e0.elapsed_time(e1)) / frames
+    ok = bool(torch.isfinite(rgb).all()) and tuple(rgb.shape) == (H, W, 3)
+    return {"metric": "rays/sec (64 samples/ray) render, one frame ray-sharded over the ranks", "value": H * W / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_frame": ms, "frames": frames, "scaling": "strong", "n_gpus": world,
+            "config": {"workload": f"configs[4]: one {H}x{W} frame, {N} samples/ray, contiguous ray bands of {H * W // world} rays per rank, "
+                                   f"one all_gather of (rgb, disp) = 16 B/ray on every rank"},
+            "frame_assembled_on_every_rank": ok, "clocks": c.sampler.window(t_begin, t_end) if c.sampler else None}
+
+
+def bench_train(args, c, B, N, steps, warmup, loop_api=False):
+    """BASELINE configs[2] / configs[4]: training step, B rays x N samples per GPU, fwd+bwd+Adam, data-parallel
     with one all-reduce of the flat gradient buffer per step (weak scaling)."""
     import torch
-    import torch.distributed as dist
-    from nerf_simple_b200 import _lib, ops
+    from nerf_simple_b200 import ops
     from nerf_simple_b200.nets import Nerf
     from nerf_simple_b200.trainer import Trainer
     from nerf_simple_b200.xyz import poses_to_render
-
-    _lib.load()
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, N = args.batch, args.samples
+    dev, world, rank = c.dev, c.world, c.rank
     f = 400 / (2 * np.tan(FOV / 2))
     torch.manual_seed(0)
     net = Nerf().to(dev)
     poses = torch.stack(poses_to_render(4, -30, 25)).to(dev)          # 25 half-res training views (lego.yaml)
     rays_table = ops.generate_rays(poses, 400, 400, f)                 # 4.0 M rays, device resident
-    g = torch.Generator(device=dev); g.manual_seed(2 + rank)
+    g = torch.Generator(device=dev); g.manual_seed(2)
     gt_table = torch.rand((rays_table.shape[0], 3), device=dev, generator=g)
-    tr = Trainer(net, rays_table, gt_table, N=N, batch_size=B, seed=1 + rank, precision=args.precision, world_size=world)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(args.warmup):
+    tr = Trainer(net, rays_table, gt_table, N=N, batch_size=B, seed=1, precision=args.precision, world_size=world)
+    for _ in range(warmup):
         tr.step()
-    sync_all()
+    c.sync_all()
     l0 = tr.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        loss = tr.step()                             # single GPU: one CUDA-graph replay per step
+    for _ in range(steps):
+        tr.step()                                    # one CUDA-graph replay per step
     e1.record()
     timed_launches = tr.launches - l0
-    sync_all()
+    c.sync_all()
     t_end = time.perf_counter()
-    clocks = sampler.stop(t_begin, t_end) if sampler else None
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = c.max_over_ranks(e0.elapsed_time(e1)) / steps
     value = world * B / (ms_step * 1e-3)
-    # e2e: the loss of every step is read back on the host (loss.item(), train.py:61-63), rays/colours
-    # selected by index on the device like the timed loop (the tables are the step's resident inputs)
-    sync_all()
+    # ---- e2e, train.py's own data flow (train.py:47-51): the batch is chosen on the HOST and arrives in pinned host
+    # memory (rays 24 B + colours 12 B per ray), is copied to the device inside the timed region, and the loss is read
+    # back every step (loss.item(), train.py:61-63)
+    pool = 8
+    ids = torch.randint(0, rays_table.shape[0], (pool, B), generator=torch.Generator().manual_seed(3 + rank))
+    rays_h = [rays_table[ids[i].to(dev)].cpu().pin_memory() for i in range(pool)]
+    gt_h = [gt_table[ids[i].to(dev)].cpu().pin_memory() for i in range(pool)]
+    for i in range(4):
+        tr.step(sync_loss=True, rays=rays_h[i % pool], gt=gt_h[i % pool])
+    c.sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lv = tr.step(sync_loss=True)
-    sync_all()
-    e2e = world * B * args.steps / (time.perf_counter() - t0)
-    for _ in range(min(20, args.steps)):             # per-part times from eager launches with events around the two MLP calls
+    for i in range(steps):
+        lv = tr.step(sync_loss=True, rays=rays_h[i % pool], gt=gt_h[i % pool])
+    c.sync_all()
+    e2e = world * B * steps / c.max_over_ranks(time.perf_counter() - t0)
+    launch_mode = tr.launch_mode
+    for _ in range(min(20, steps)):                  # per-part times from eager launches with events around the two MLP calls
         tr.step(time_parts=True)
     torch.cuda.synchronize(dev)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in tr.part_events]))
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in tr.part_events]))
-    # ---- the reference's own training loop body, unchanged calls (train.py:47-57): rg.select -> CPU gather of
-    # the ground truth -> render_nerf (autograd) -> MSELoss -> backward -> torch.optim.Adam, host tensors in
-    loop_val = None
-    if world == 1:
+    pk = load_peaks()
+    M = B * N
+    achieved = FLOP_TRAIN * M / (ms_step * 1e-3) / 1e12
+    traffic, tsrc = load_traffic("train_step_backward") if (B, N) == (4096, 64) else (None, None)
+    rec = {"metric": "rays/sec (64 samples/ray) train", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms_step, "scaling": "weak", "dtype": args.precision, "samples_per_sec": value * N,
+           "config": {"workload": f"training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, fused compositing backward "
+                                  f"(train.py:47-57)", "rays_table": "25 views 400x400 (4.0 M rays) on device",
+                      "parallelism": f"data-parallel over {world} rank(s), one all-reduce of 595,844 fp32 grads/step",
+                      "launch": launch_mode, "l2": f"saved activations + deltas per step = {M * 10e3 / 1e9:.1f} GB (larger than L2)"},
+           "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": B * 36, "d2h_bytes_per_step": 4,
+                   "api": "Trainer.step(rays=pinned, gt=pinned, sync_loss=True): host-selected batch copied in, loss read back, every step"},
+           "gpu_launches": timed_launches,
+           "roofline": {"kernel": "whole step (chain_kernel<FwdEpi<save>> + backward kernels; the MLP is >99 % of the FLOPs)", "bound": "tensor",
+                        "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
+                        "peak_burst": pk["burst"], "frac_burst": achieved / pk["burst"], "flop_per_step": FLOP_TRAIN * M,
+                        "peak_source": pk["source"] + ", sustained figure", "traffic": traffic, "traffic_source": tsrc},
+           "mlp_forward_ms": fwd_ms, "mlp_backward_ms": bwd_ms,
+           "mlp_forward_tflops": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12,
+           "mlp_backward_tflops": (FLOP_TRAIN - FLOP_FWD) * M / (bwd_ms * 1e-3) / 1e12,
+           "clocks": c.sampler.window(t_begin, t_end) if c.sampler else None, "final_loss": float(lv)}
+    if loop_api and world == 1:
+        # ---- the reference's own training loop body, unchanged calls (train.py:47-57): rg.select -> CPU gather of
+        # the ground truth -> render_nerf (autograd) -> MSELoss -> backward -> torch.optim.Adam, host tensors in
         from nerf_simple_b200 import config
         from nerf_simple_b200.dataload import RayGenerator
         from nerf_simple_b200.rendering import render_nerf
@@ -389,83 +531,119 @@ def train_arm(args, rank, local_rank, world):
             loss2.backward()
             opt.step()
             return loss2
-        for _ in range(10):                          # the autograd path allocates its 2.6 GB of workspaces here
+        for _ in range(10):                          # the autograd path allocates its workspaces here
             loop_step()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        reps = max(10, args.steps // 2)
+        reps = max(10, steps // 4)
         for _ in range(reps):
             l2 = loop_step()
         l2.item()
         torch.cuda.synchronize(dev)
-        loop_val = reps * B / (time.perf_counter() - t0)
+        rec["e2e_train_py_loop"] = {"value": reps * B / (time.perf_counter() - t0), "unit": "rays/s", "h2d_bytes_per_step": B * 12,
+                                    "d2h_bytes_per_step": B * 8,
+                                    "api": "train.py:47-57 body unchanged: rg.select (device mode) -> train_imgs[ray_ids].cuda() -> render_nerf "
+                                           "-> MSELoss -> backward -> torch.optim.Adam"}
         config.set_select("reference"); config.set_sampler("reference")
+    del tr, rays_table, gt_table
+    torch.cuda.empty_cache()
+    return rec
+
+
+def b200_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    c = setup(args, local_rank, world)
+    H = W = args.res
+    N = args.samples
+    pk = load_peaks()
+    if args.workload == "train":
+        rec = bench_train(args, c, args.batch, N, args.steps, max(args.warmup, 20), loop_api=True)
+        if rank == 0:
+            rec.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+            print(json.dumps(rec), flush=True)
+        if c.sampler:
+            c.sampler.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    r = bench_render(args, c, H, W, N, args.steps, args.warmup, fine=args.fine, fused=(args.render_path == "fused"))
+    M = H * W * N
+    achieved = FLOP_FWD * M / (r["mlp_ms"] * 1e-3) / 1e12
+    kernel_key = "chain_kernel<FwdEpi<render>>" if r["fused"] else "chain_kernel<FwdEpi<false>>"
+    traffic, tsrc = load_traffic(kernel_key) if (H, W, N) == (800, 800, 64) else (None, None)
+    cfg = workload_config(H, W, N, world)
+    line = {
+        "metric": METRIC, "value": r["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "samples_per_sec": r["value"] * N,
+        "config": cfg,
+        "detail": {"N_fine": args.fine, "sampler": "device Philox seed 1",
+                   "render_path": ("one kernel per frame (camera -> sampler -> MLP -> compositing in chain_kernel<FwdEpi<render>>)"
+                                   if r["fused"] else "4 kernels per frame: raygen, Philox sampler, fused posenc+MLP, compositing")},
+        "e2e": {"value": r.get("e2e"), "unit": "rays/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 16,
+                "api": "FrameRenderer.render_frame_host(pose_pinned) -> pinned fp32 rgb + disparity frame"},
+        "e2e_video_u8": {"value": r.get("e2e_u8"), "unit": "rays/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": H * W * 3,
+                         "api": "FrameRenderer.render_frame_u8_host: clip + BGR + uint8 on the device (render_poses' video frames)"},
+        "e2e_render_image_api": {"value": r.get("api"), "unit": "rays/s", "h2d_bytes_per_step": H * W * 24, "d2h_bytes_per_step": H * W * 16,
+                                 "api": f"render_image(net, rg, batch_size={REF_CHUNK}): CPU ray table, {H * W // REF_CHUNK} chunks, CPU frame"},
+        "gpu_launches": r["gpu_launches"],
+        "roofline": {"kernel": kernel_key + " (fused posenc+MLP, tcgen05 cta_group::2)", "bound": "tensor", "achieved": achieved,
+                     "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "peak_burst": pk["burst"],
+                     "frac_burst": achieved / pk["burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                     "kernel_ms": r["mlp_ms"], "flop_per_launch": FLOP_FWD * M, "traffic": traffic, "traffic_source": tsrc},
+        "clocks": c.sampler.window(*r["t_window"]) if c.sampler else None, "outputs_finite": r.get("finite"),
+    }
+    if args.workload == "all" and args.fine == 0:
+        # sub-records of the same run (every rank takes part; rank 0 prints)
+        line["train"] = bench_train(args, c, 4096, N, args.train_steps, 20, loop_api=True)
+        line["train_dp8192"] = bench_train(args, c, 8192, N, max(100, args.train_steps // 2), 20)
+        line["sharded_frame"] = bench_sharded_frame(args, c, 1600, 1600, N, frames=max(3, args.steps // 4))
+        r128 = bench_render(args, c, H, W, 128, max(3, args.steps // 4), 2, e2e=False, api=False)
+        line["n128"] = {"value": r128["value"], "unit": "rays/s", "ms_per_step": r128["ms_per_step"], "samples_per_sec": r128["value"] * 128,
+                        "mlp_tflops": FLOP_FWD * H * W * 128 / (r128["mlp_ms"] * 1e-3) / 1e12,
+                        "config": f"same frames at the reference's default N=128 (configs/lego.yaml:6, utils/rendering.py:102,145)"}
     if rank == 0:
-        pk = load_peaks()
-        M = B * N
-        achieved = FLOP_TRAIN * M / (ms_step * 1e-3) / 1e12
-        line = {"metric": "rays/sec (64 samples/ray) train", "value": value, "unit": "rays/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "samples_per_sec": value * N,
-                "config": {"workload": f"configs[2]: training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, "
-                                       f"fused compositing backward", "rays_table": "25 views 400x400 (4.0 M rays) on device",
-                           "parallelism": f"data-parallel over {world} rank(s), one all-reduce of 595,844 fp32 grads/step",
-                           "launch": ("eager launches" if tr._graph is None else ("CUDA-graph replay of the whole step" if len(tr._graph) == 1
-                                      else "two CUDA graphs per step around the eagerly launched NCCL all-reduce")),
-                           "l2": "saved activations + deltas per step = 2.6 GB (larger than L2)"},
-                "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
-                        "api": "Trainer.step(sync_loss=True): loss read back every step"},
-                "e2e_train_py_loop": {"value": loop_val, "unit": "rays/s", "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": B * 8,
-                                      "api": "train.py:47-57 body unchanged: rg.select (device mode) -> train_imgs[ray_ids].cuda() -> render_nerf "
-                                             "-> MSELoss -> backward -> torch.optim.Adam"},
-                "gpu_launches": timed_launches,
-                "roofline": {"kernel": "whole step (fwd+dgrad+wgrad chain kernels dominate)", "bound": "tensor",
-                             "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
-                             "peak_burst": pk["burst"], "flop_per_step": FLOP_TRAIN * M, "traffic": None},
-                # the backward (delta chain + wgrad) is HBM-bound: saved bf16 activations and deltas are the traffic
-                "roofline_backward": {"kernel": "chain_kernel<DgradEpi> + mlp_wgrad_tc_kernel", "bound": "hbm",
-                                      "achieved": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                      "frac": BWD_BYTES * M / (bwd_ms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": bwd_ms,
-                                      "bytes_per_sample": BWD_BYTES,
-                                      "traffic": 5383000000 if (B, N) == (4096, 64) else None,
-                                      "traffic_source": "dram bytes of one dgrad + one wgrad launch, profiles/r1c_train_kernels_ncu.txt (2.522 GB delta chain + 2.861 GB wgrad)"},
-                "roofline_forward": {"kernel": "chain_kernel<FwdEpi<save>>", "bound": "tensor", "achieved": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12,
-                                     "peak": pk["sustained"], "unit": "TFLOP/s", "frac": FLOP_FWD * M / (fwd_ms * 1e-3) / 1e12 / pk["sustained"],
-                                     "kernel_ms": fwd_ms},
-                "clocks": clocks, "final_loss": float(lv)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_subprocess(args)
+            try:
+                line["reference_gpu_eager"] = reference_gpu_eager(H, W, N, c.dev)
+            except Exception as e:
+                line["reference_gpu_eager"] = {"value": None, "error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
+    if c.sampler:
+        c.sampler.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="render", choices=["render", "train"])
+    ap.add_argument("--workload", default="all", choices=["all", "render", "train"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20 frames for render, 500 steps for train)")
+    ap.add_argument("--steps", type=int, default=20, help="timed steps (frames of the headline render workload)")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--train-steps", type=int, default=400, help="timed steps of the train sub-records")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--res", type=int, default=800)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="reference arm: skip the configs[0] extras")
     ap.add_argument("--fine", type=int, default=0, help="extension: fine samples per ray (64 coarse + N fine)")
     ap.add_argument("--render-path", default="separate", choices=["separate", "fused"],
                     help="separate: raygen, sampler, fused posenc+MLP, compositing kernels; fused: one kernel per frame")
     args = ap.parse_args()
-    if args.steps is None:      # a train step is ~1.3 ms: enough of them for nvidia-smi to sample the clocks in the timed region
-        args.steps = 500 if (args.workload == "train" and args.impl == "b200") else 20
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "train" and args.steps == 20:
+        args.steps = 500            # a train step is ~1 ms: enough of them for nvidia-smi to sample the clocks
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_arm(args, rank)
-        return
-    if args.workload == "train":
-        train_arm(args, rank, local_rank, world)
         return
     b200_arm(args, rank, local_rank, world)
 

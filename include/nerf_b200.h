@@ -147,6 +147,13 @@ int nb200_render_camera(int precision, const float* poses, int P, int H, int W, 
                         int64_t n_rays, uint64_t seed, uint64_t offset, int N, float tn, float tf,
                         const void* packed, float* rgb, float* disp, float* acc, nb200_stream_t stream);
 
+/* Video-frame conversion for the render loops.  Replaces the clip of utils/rendering.py:146 followed by
+ * cv2.cvtColor(RGB2BGR) and (frame*255).astype(np.uint8) of :158-159 (bgr != 0), or the same without the
+ * channel swap (bgr == 0): out[p, c'] = trunc(255 * clamp(rgb[p, c], 0, 1)) with c' = 2 - c for BGR.
+ * rgb dev [n_pixels,3] fp32 (unclipped or clipped), out dev [n_pixels,3] uint8: a frame leaves the device as
+ * 3 B/pixel instead of 12. */
+int nb200_frame_to_u8(const float* rgb, int64_t n_pixels, int bgr, uint8_t* out, nb200_stream_t stream);
+
 /* EXTENSION (no reference counterpart: hierarchical sampling is "not implemented yet" in the
  * reference, configs/lego.yaml:7).  Inverse-CDF importance sampler of the NeRF paper (sec. 5.2):
  * pdf = weights[:,1:-1] + 1e-5 over the mid-point bins of ts [B,Nc], Nf samples per ray drawn with

@@ -14,13 +14,13 @@ int record_cuda_error(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[64];   // per device; racing writers store the same value
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     return 148;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 

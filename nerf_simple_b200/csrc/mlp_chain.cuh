@@ -26,7 +26,7 @@ constexpr int kCProducerWarp = 16, kCMmaWarp = 17;
 // barrier offsets inside the barrier block
 constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128;
 
-__constant__ float c_f32[kF32Floats];  // biases / head weights of the net being run (uploaded per call)
+__constant__ float c_f32[kConstSlots * kF32Floats];  // biases / head weights of the nets being run (slot per packed buffer, uploaded per call)
 
 struct TileCtx {
   int64_t tile;      // 128-row tile index
@@ -36,6 +36,7 @@ struct TileCtx {
   uint32_t rowoff;   // r * 128
   uint32_t r7s;      // (r & 7) << 4
   uint32_t a_img, e_img, t_lane;
+  const float* cf;   // this launch's slot of the constant bank
 };
 __device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32_t j) {
   return kb * 16384u + c.rowoff + ((j << 4) ^ c.r7s);
@@ -93,6 +94,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     c.a_img = smem_base + kC_A + slot * kABytes;
     c.e_img = smem_base + kC_E + slot * kEBytes;
     c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
+    c.cf = c_f32 + p.cslot * kF32Floats;
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
     uint32_t acc_parity = 0;
     typename Epi::State st;
@@ -253,6 +255,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
 struct FwdEpiParams {
   CUtensorMap tmap128, tmap64;  // packed weight image as [rows x 128 B], boxes of 128 / 64 rows
   int dbg;
+  int cslot;       // constant-bank slot holding this net's fp32 tail
   unsigned long long* dbg_counters;
   int in_mode;
   const float* in0;
@@ -386,8 +389,8 @@ __device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint
 template <bool kRelu, bool kSigma, bool kSave>
 __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, uint8_t* gsave,
                                            float& sigma) {
-  const float* b = c_f32 + bias_off + col0;
-  const float* ws = c_f32 + kF32WSig + col0;
+  const float* b = c.cf + bias_off + col0;
+  const float* ws = c.cf + kF32WSig + col0;
   const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -496,8 +499,8 @@ struct FwdEpi {
         uint32_t a[32];
         tmem_ld32(c.t_lane + col0, a);
         tmem_ld_wait();
-        const float* b = c_f32 + kF32Bias + 9 * 256 + col0;
-        const float* w = c_f32 + kF32WC1 + col0;
+        const float* b = c.cf + kF32Bias + 9 * 256 + col0;
+        const float* w = c.cf + kF32WC1 + col0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x[8];
@@ -519,8 +522,8 @@ struct FwdEpi {
       if (c.half == 0) {
         float4 o;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xaddr));
-        const float4 res = make_float4(rgb[0] + o.x + c_f32[kF32BC1], rgb[1] + o.y + c_f32[kF32BC1 + 1], rgb[2] + o.z + c_f32[kF32BC1 + 2],
-                                       st.sigma + o.w + c_f32[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
+        const float4 res = make_float4(rgb[0] + o.x + c.cf[kF32BC1], rgb[1] + o.y + c.cf[kF32BC1 + 1], rgb[2] + o.z + c.cf[kF32BC1 + 2],
+                                       st.sigma + o.w + c.cf[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
         if (kRender) {
           // stage the row for the compositing warps in A[slot]: its last reader (color_fc.0's MMAs) is done and
           // the next writer (layer 0's epilogue of the next tile) runs only after every warp of the slot has
@@ -585,7 +588,7 @@ struct DgradEpi {
     // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
     const uint8_t* c1img = p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768;
     uint8_t* dsave = p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768;
-    const float* w = c_f32 + kF32WC1;
+    const float* w = c.cf + kF32WC1;
     const uint32_t kb = (uint32_t)c.half;  // 128 columns: each half of the slot's threads takes 64
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -633,7 +636,7 @@ struct DgradEpi {
       uint32_t a[32];
       tmem_ld32(c.t_lane + col0, a);
       tmem_ld_wait();
-      const float* ws = c_f32 + kF32WSig + col0;
+      const float* ws = c.cf + kF32WSig + col0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float x[8];

@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "stream_common.cuh"
 #include "tc_common.cuh"
@@ -49,10 +51,22 @@ struct PackedLayout {
 };
 constexpr int kF32Bias = 0, kF32WSig = 2560, kF32BSig = 2816, kF32WC1 = 2820, kF32BC1 = 3204,
               kF32Floats = 3264;
+constexpr int kConstSlots = 4;   // constant-bank copies of the fp32 tail (4 x 13 KB): concurrent nets never share one
 
 __constant__ PackedLayout c_layout;
 static PackedLayout h_layout;
-static bool h_layout_ready = false;
+static bool h_layout_built = false;
+
+// Everything CUDA caches per device (constant-bank copies, function attributes, the architecture check) is keyed
+// by the current device, so one process can drive several GPUs; the tables are guarded by one mutex.
+constexpr int kMaxDevices = 64;
+struct DeviceState { bool layout_uploaded, attr_fwd, attr_render, attr_bwd; int arch; };
+static DeviceState g_dev[kMaxDevices];
+static std::mutex g_mu;
+static int current_device(int* dev) {
+  NB_CUDA_CHECK(cudaGetDevice(dev));
+  return (*dev >= 0 && *dev < kMaxDevices) ? NB200_OK : NB200_ERR_UNSUPPORTED;
+}
 
 __host__ __device__ constexpr int mma_layer_of(int ml) {
   return ml <= 4 ? L0_0 + ml : (ml == 5 ? L_SKIP : (ml <= 7 ? L1_0 + (ml - 6) : (ml == 8 ? L_2 : L_C0)));
@@ -115,11 +129,17 @@ static void build_layout() {
   h_layout.total_bytes = t.off + kF32Floats * (uint32_t)sizeof(float);
 }
 
+static void ensure_host_layout() {   // caller holds g_mu
+  if (!h_layout_built) { build_layout(); h_layout_built = true; }
+}
 static int ensure_layout() {
-  if (h_layout_ready) return NB200_OK;
-  build_layout();
-  NB_CUDA_CHECK(cudaMemcpyToSymbol(c_layout, &h_layout, sizeof(PackedLayout)));
-  h_layout_ready = true;
+  int dev = 0;
+  NB_TRY_RC(current_device(&dev));
+  std::lock_guard<std::mutex> lock(g_mu);
+  ensure_host_layout();
+  if (g_dev[dev].layout_uploaded) return NB200_OK;
+  NB_CUDA_CHECK(cudaMemcpyToSymbol(c_layout, &h_layout, sizeof(PackedLayout)));   // this device's constant bank
+  g_dev[dev].layout_uploaded = true;
   return NB200_OK;
 }
 
@@ -228,7 +248,8 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
 
 // ------------------------------------------------------------------------------ host API
 size_t tc_packed_bytes() {
-  if (!h_layout_ready) build_layout();  // layout is host-computable without a device
+  std::lock_guard<std::mutex> lock(g_mu);
+  ensure_host_layout();  // layout is host-computable without a device
   return h_layout.total_bytes;
 }
 // Training tensors are laid out for an EVEN number of 128-sample tiles: the chain kernels work on pair-tiles
@@ -272,16 +293,55 @@ int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s) {
 }
 
 static int check_arch() {
-  static int arch = 0;
-  if (arch == 0) arch = nb200_device_arch();
+  int dev = 0;
+  NB_TRY_RC(current_device(&dev));
+  int arch;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_dev[dev].arch == 0) g_dev[dev].arch = nb200_device_arch();
+    arch = g_dev[dev].arch;
+  }
   if (arch < 0) return NB200_ERR_CUDA;
   return (arch / 10 == 10) ? NB200_OK : NB200_ERR_ARCH;
 }
+// cudaFuncSetAttribute is per device: `which` selects the flag of the current device's DeviceState
+template <class F>
+static int ensure_attr(bool DeviceState::*which, F&& set) {
+  int dev = 0;
+  NB_TRY_RC(current_device(&dev));
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (g_dev[dev].*which) return NB200_OK;
+  NB_TRY_RC(set());
+  g_dev[dev].*which = true;
+  return NB200_OK;
+}
 
-// biases / head weights of the net being run go to the constant bank (stream-ordered D2D copy)
-static int upload_consts(const void* packed, cudaStream_t s) {
+// Biases / head weights of the net being run go to the constant bank (stream-ordered D2D copy in front of the
+// launch).  The bank holds kConstSlots copies, assigned per (device, packed buffer): nets that run concurrently
+// from different streams or threads (coarse + fine, two trainers) use different slots and cannot overwrite each
+// other's biases; a slot is recycled (round robin) only when more than kConstSlots packed buffers are in use on a
+// device, and then only stream order protects it -- NB200_ERR_UNSUPPORTED is not raised for that, it is documented.
+struct ConstSlotEntry { const void* packed; int dev; };
+static ConstSlotEntry g_slots[kConstSlots];
+static int g_slot_next = 0;
+static int upload_consts(const void* packed, cudaStream_t s, int* slot_out) {
+  int dev = 0;
+  NB_TRY_RC(current_device(&dev));
+  int slot = -1;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (int i = 0; i < kConstSlots; ++i)
+      if (g_slots[i].packed == packed && g_slots[i].dev == dev) slot = i;
+    if (slot < 0) {
+      slot = g_slot_next;
+      g_slot_next = (g_slot_next + 1) % kConstSlots;
+      g_slots[slot].packed = packed; g_slots[slot].dev = dev;
+    }
+  }
   NB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_f32, reinterpret_cast<const uint8_t*>(packed) + h_layout.f32_off,
-                                        kF32Floats * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+                                        kF32Floats * sizeof(float), (size_t)slot * kF32Floats * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
+  *slot_out = slot;
   return NB200_OK;
 }
 
@@ -291,12 +351,15 @@ static int upload_consts(const void* packed, cudaStream_t s) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-struct TmapPair { const void* packed; CUtensorMap m128, m64; };
-static int get_tmaps(const void* packed, const TmapPair** out) {
+struct TmapPair { const void* packed; int dev; CUtensorMap m128, m64; };
+static int get_tmaps(const void* packed, TmapPair* out) {   // returns a COPY: the cache entry may be recycled by another thread
+  int dev = 0;
+  NB_TRY_RC(current_device(&dev));
+  std::lock_guard<std::mutex> lock(g_mu);
   static TmapPair cache[8];
   static int used = 0, next = 0;
   for (int i = 0; i < used; ++i)
-    if (cache[i].packed == packed) { *out = &cache[i]; return NB200_OK; }
+    if (cache[i].packed == packed && cache[i].dev == dev) { *out = cache[i]; return NB200_OK; }
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -323,7 +386,8 @@ static int get_tmaps(const void* packed, const TmapPair** out) {
     }
   }
   t.packed = packed;
-  *out = &t;
+  t.dev = dev;
+  *out = t;
   return NB200_OK;
 }
 
@@ -339,22 +403,23 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
                float* out, void* saved, void*, size_t, cudaStream_t s) {
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
-  static bool attr_set = false;
-  if (!attr_set) {
+  NB_TRY_RC(ensure_attr(&DeviceState::attr_fwd, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
-    attr_set = true;
-  }
+    return NB200_OK;
+  }));
   const int64_t T = saved ? train_tiles(M) : ceil_div64(M, kTileM);
-  NB_TRY_RC(upload_consts(packed, s));
-  const TmapPair* tm = nullptr;
-  NB_TRY_RC(get_tmaps(packed, &tm));
   FwdEpiParams p;
-  p.tmap128 = tm->m128; p.tmap64 = tm->m64;
-  { const char* e = getenv("NB200_DBG"); p.dbg = e ? atoi(e) : 0; }
+  NB_TRY_RC(upload_consts(packed, s, &p.cslot));
+  TmapPair tm;
+  NB_TRY_RC(get_tmaps(packed, &tm));
+  p.tmap128 = tm.m128; p.tmap64 = tm.m64;
+  p.dbg = 0;
   p.dbg_counters = nullptr;
+#ifdef NB200_DEV   // developer probe (synchronises, allocates, prints): never in the shipped library
+  { const char* e = getenv("NB200_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.dbg & 8) {
     static unsigned long long* ctr = nullptr;
     if (!ctr) { cudaMalloc(&ctr, 64); }
@@ -364,6 +429,7 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
     cudaMemset(ctr, 0, 64);
     p.dbg_counters = ctr;
   }
+#endif
   p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
   p.nshift = (N > 0 && (N & (N - 1)) == 0) ? __builtin_ctz((unsigned)N) : -1;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
@@ -386,19 +452,18 @@ int tc_render(const float* rays, const float* poses, int H, int W, float f, int6
               cudaStream_t s) {
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
-  static bool attr_set = false;
-  if (!attr_set) {
+  NB_TRY_RC(ensure_attr(&DeviceState::attr_render, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
-    attr_set = true;
-  }
+    return NB200_OK;
+  }));
   const int64_t M = B * N, T = ceil_div64(M, kTileM);
-  NB_TRY_RC(upload_consts(packed, s));
-  const TmapPair* tm = nullptr;
-  NB_TRY_RC(get_tmaps(packed, &tm));
   FwdEpiParams p;
   memset(&p, 0, sizeof(p));
-  p.tmap128 = tm->m128; p.tmap64 = tm->m64;
+  NB_TRY_RC(upload_consts(packed, s, &p.cslot));
+  TmapPair tm;
+  NB_TRY_RC(get_tmaps(packed, &tm));
+  p.tmap128 = tm.m128; p.tmap64 = tm.m64;
   p.in_mode = rays ? NB200_IN_RAYS : kInCamera; p.in0 = rays; p.in1 = ts; p.M = M; p.N = N;
   p.nshift = (N > 0 && (N & (N - 1)) == 0) ? __builtin_ctz((unsigned)N) : -1;
   p.packed = reinterpret_cast<const uint8_t*>(packed);
@@ -416,12 +481,11 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
   if (!scratch || scratch_bytes < tc_scratch_bytes(M, 1)) return NB200_ERR_WORKSPACE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  NB_TRY_RC(ensure_attr(&DeviceState::attr_bwd, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
-    attr_set = true;
-  }
+    return NB200_OK;
+  }));
   const int64_t T = train_tiles(M);
   const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
   uint8_t* ds = reinterpret_cast<uint8_t*>(scratch);
@@ -433,10 +497,10 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
   bp.d_out = d_out; bp.dscr = ds;
   {
-    NB_TRY_RC(upload_consts(packed, s));
-    const TmapPair* tm = nullptr;
+    NB_TRY_RC(upload_consts(packed, s, &bp.cslot));
+    TmapPair tm;
     NB_TRY_RC(get_tmaps(packed, &tm));
-    bp.tmap128 = tm->m128; bp.tmap64 = tm->m64;
+    bp.tmap128 = tm.m128; bp.tmap64 = tm.m64;
     chain_kernel<DgradEpi><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
     NB_LAUNCH_CHECK("chain_kernel<DgradEpi>");
   }
@@ -498,7 +562,9 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     if (w.head == 2) c = 83;
     w.cost = c;
   }
-  { const char* e = getenv("NB200_WG_ONLY"); if (e) { const int k = atoi(e); if (k >= 0 && k < n) { wp.items[0] = wp.items[k]; n = 1; } } }  // developer probe: time one item alone
+#ifdef NB200_DEV   // developer probe: time one item alone (leaves the other gradients at zero -- never in the shipped library)
+  { const char* e = getenv("NB200_WG_ONLY"); if (e) { const int k = atoi(e); if (k >= 0 && k < n) { wp.items[0] = wp.items[k]; n = 1; } } }
+#endif
   wp.num_items = n;
   mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");

@@ -37,9 +37,12 @@ class FrameRenderer:
         self.mlp_events = []       # optional (start, stop) CUDA events around the MLP kernel
         self._copy_stream, self._last_copy = None, None
 
-    def render_rays(self, poses_dev, ray_begin, n_rays, time_mlp=False):
+    def render_rays(self, poses_dev, ray_begin, n_rays, time_mlp=False, philox_base=None):
         """rgb [n,3] clipped to [0,1] and disparity [n] for rays [ray_begin, ray_begin+n) of the
-        pose table `poses_dev` ([P,4,4] on the device)."""
+        pose table `poses_dev` ([P,4,4] on the device).  philox_base: position of the first sample of this call
+        in the jitter stream (default: continue where the previous call stopped)."""
+        if philox_base is not None:
+            self._offset = int(philox_base)
         with torch.no_grad():
             if self.fused:
                 if time_mlp:
@@ -81,6 +84,11 @@ class FrameRenderer:
             self.launches += 7
             return rgb.clamp_(0.0, 1.0), disp
 
+    def frame_quads(self):
+        """Philox calls (4 draws each) one whole frame consumes."""
+        n = self.H * self.W
+        return (n * self.N + 3) // 4 + (n * self.Nf + 3) // 4
+
     def render_frame(self, poses_dev, idx=0, time_mlp=False):
         n = self.H * self.W
         rgb, disp = self.render_rays(poses_dev, idx * n, n, time_mlp)
@@ -114,6 +122,17 @@ class FrameRenderer:
         self._last_copy = done
         return done
 
+    def render_frame_u8_host(self, pose_cpu_pinned, out_u8_pinned, bgr=True):
+        """Video path (render_poses, utils/rendering.py:139-160): pose (pinned [4,4]) in, uint8 frame [H,W,3] (pinned)
+        out, clipped / BGR-swapped / quantised on the device -- 3 B/pixel cross PCIe instead of 16."""
+        pose = pose_cpu_pinned.to(self.device, non_blocking=True).view(1, 4, 4)
+        rgb, _ = self.render_frame(pose, 0)
+        u8 = ops.frame_to_u8(rgb, bgr=bgr)
+        self.launches += 1
+        out_u8_pinned.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_u8_pinned
+
     def finish(self):
         """Block until every frame handed to render_frame_host(wait=False) is on the host."""
         if self._last_copy is not None:
@@ -124,6 +143,10 @@ def gather_shards(local, n_items, rank, world, group=None):
     """all_gather of per-rank row blocks whose sizes follow `shard_range` (they differ by at most one
     row, so every rank pads to the largest block; collectives need equal sizes)."""
     import torch.distributed as dist
+    if n_items % world == 0:     # equal bands (every lego size: 1600^2 / 8, 800^2 / 8, ...): one collective into one buffer
+        full = local.new_empty((n_items,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+        return full
     spans = [shard_range(n_items, r, world) for r in range(world)]
     width = max(e - b for b, e in spans)
     padded = local
@@ -136,11 +159,18 @@ def gather_shards(local, n_items, rank, world, group=None):
 
 def render_sharded(renderer: FrameRenderer, poses_dev, idx, rank, world, gather=True):
     """Ray-sharded render of frame `idx`: each rank renders a contiguous band of rays; one
-    all_gather of (rgb, disp) = 16 B/ray assembles the frame on every rank."""
+    all_gather of (rgb, disp) = 16 B/ray assembles the frame on every rank.  Every sample keeps the place in the
+    jitter stream it has in the unsharded frame (the Philox position is a function of the ray's index in the frame),
+    so for N % 4 == 0 the assembled frame is bit-identical to the one a single GPU renders."""
     n = renderer.H * renderer.W
     b, e = shard_range(n, rank, world)
-    rgb, disp = renderer.render_rays(poses_dev, idx * n + b, e - b)
-    if not gather or world == 1:
+    base = renderer._offset
+    exact = renderer.net_fine is None and (b * renderer.N) % 4 == 0
+    rgb, disp = renderer.render_rays(poses_dev, idx * n + b, e - b, philox_base=base + (b * renderer.N) // 4 if exact else None)
+    renderer._offset = base + renderer.frame_quads()          # every rank advances by one whole frame
+    if world == 1:
+        return rgb.view(renderer.H, renderer.W, 3), disp.view(renderer.H, renderer.W)
+    if not gather:
         return rgb, disp
     full = gather_shards(torch.cat([rgb, disp[:, None]], dim=1), n, rank, world)     # [n, 4]
     return full[:, :3].reshape(renderer.H, renderer.W, 3), full[:, 3].reshape(renderer.H, renderer.W)

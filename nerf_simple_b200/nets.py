@@ -42,6 +42,11 @@ class Nerf(nn.Module):
         """The 24 parameter tensors in state_dict order (what the C ABI expects)."""
         return list(self.parameters())
 
+    def invalidate_packed(self):
+        """Call after changing weights through `.data` (see PackedWeights.invalidate): the kernel-format bf16 copy
+        is keyed on the parameters' version counters, which such writes bypass."""
+        self._packed.invalidate()
+
     def forward(self, v):
         """v: [M,6] (x,y,z,d1,d2,d3) on the GPU -> [M,4] raw (r,g,b,sigma).  utils/nets.py:34-43."""
         return mlp_apply(self, _lib.IN_POINTS, v)

@@ -58,6 +58,12 @@ class PackedWeights:
         self.buf = None
         self.key = None
 
+    def invalidate(self):
+        """Force a re-pack on the next call.  Needed after writes the version counters do not see: `p.data.copy_()`,
+        `p.data.normal_()`, EMA swaps through `.data` (in-place ops on the parameter itself, `optimizer.step()` and
+        `load_state_dict` bump the version and need nothing)."""
+        self.key = None
+
     def get(self, params, precision):
         if precision == _lib.FP32:
             return None
@@ -283,6 +289,17 @@ def render_fused(net, N, rays=None, ts=None, poses=None, H=0, W=0, f=0.0, ray_be
                                      _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), st)
         _lib.check(rc, "nb200_render_camera")
     return rgb, disp, acc
+
+
+def frame_to_u8(rgb, bgr=True):
+    """rgb [...,3] fp32 (CUDA) -> uint8 of the same shape: clip to [0,1], optional RGB->BGR swap, x255, truncate --
+    the frame cv2.VideoWriter receives at utils/rendering.py:158-159, converted on the device (3 B/pixel to copy)."""
+    lib = _lib.load()
+    rgb = _f32c(rgb, "rgb")
+    out = torch.empty(rgb.shape, dtype=torch.uint8, device=rgb.device)
+    rc = lib.nb200_frame_to_u8(_lib.ptr(rgb), rgb.numel() // 3, 1 if bgr else 0, _lib.ptr(out), _lib.stream_ptr(rgb.device))
+    _lib.check(rc, "nb200_frame_to_u8")
+    return out
 
 
 def positional_encoding(v, Lp=10, Ld=4):

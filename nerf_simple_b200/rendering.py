@@ -82,14 +82,16 @@ def render_image(net, rg, batch_size=64000, im_idx=0, im_set='val', N=128):
 def render_poses(net, poses, cam_params, batch_size, savepath=''):
     """Render every pose (list of 4x4 camera-to-world) at [H,W,f] and write an mp4, like
     utils/rendering.py:116-160 -- but rays are generated on the device per chunk (24 B/ray of
-    H2D traffic and the 461 MB host ray table disappear)."""
+    H2D traffic and the 461 MB host ray table disappear) and the frames are clipped, BGR-swapped and
+    quantised to uint8 on the device (:146,:158-159), so 3 B/pixel come back instead of 12.
+    Returns the float RGB frames (the reference returns None; callers that ignore it are unaffected)."""
     import cv2
     H, W, f = int(cam_params[0]), int(cam_params[1]), float(cam_params[2])
     n = H * W
     net = net.cuda()
     dev = next(net.parameters()).device
     pose_t = torch.stack([torch.as_tensor(p).float() for p in poses]).to(dev)
-    frames = []
+    frames, frames_u8 = [], []
     with torch.no_grad():
         for idx in range(len(poses)):
             rgbs, depths = [], []
@@ -102,11 +104,13 @@ def render_poses(net, poses, cam_params, batch_size, savepath=''):
                     rgb, depth = _render_chunk(rays, net, 128)
                 rgbs.append(rgb.clamp_(0.0, 1.0))
                 depths.append(depth)
-            frames.append(torch.cat(rgbs).reshape(H, W, 3).cpu().numpy())
+            frame = torch.cat(rgbs).reshape(H, W, 3)
+            frames.append(frame)
+            frames_u8.append(ops.frame_to_u8(frame, bgr=True).cpu().numpy())
     tstamp = str(time.time())
     out = cv2.VideoWriter(os.path.join(savepath, f'nerf_rgb{tstamp[-10:]}.mp4'),
                           cv2.VideoWriter_fourcc('m', 'p', '4', 'v'), 15, (H, W))   # (H,W) as in :156
-    for frame in frames:
-        out.write((cv2.cvtColor(frame, cv2.COLOR_RGB2BGR) * 255).astype(np.uint8))
+    for frame in frames_u8:
+        out.write(frame)
     out.release()
-    return frames
+    return [fr.cpu().numpy() for fr in frames]

@@ -8,10 +8,14 @@ the ray table and the ground-truth colours live on the device, a step is
 and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
 needs exactly one NCCL all-reduce of 595,844 floats per step.  Everything that varies
 from step to step lives in a 32-byte device-resident state, so after two eager warm-up steps the
-whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks, two graphs
-around the eagerly launched all-reduce).
+whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks the NCCL
+all-reduce is captured inside the graph, or -- NB200_GRAPH_ALLREDUCE=0 -- two graphs are replayed
+around the eagerly launched collective).  The batch can also be handed in by the caller
+(`step(rays=, gt=)`, pinned host tensors copied asynchronously), which is train.py's own flow.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -54,16 +58,34 @@ def allreduce_mean_(flat_grad, world_size, group=None):
 
 
 class Trainer:
+    """`seed` keys the ray selection and the jitter.  With world_size > 1 the rank is folded into it (every rank
+    must draw different rays, or the all-reduce averages identical gradients) and the parameters are broadcast
+    from rank 0 once, so replicas start identical whatever each rank's torch seed or checkpoint was -- what
+    DistributedDataParallel would enforce."""
+
     def __init__(self, net, rays_table, gt_table, N=64, batch_size=4096, lr=5e-4, lr_decay=1.0,
-                 tn=2.0, tf=6.0, seed=1, precision="bf16", world_size=1, use_graph=True):
+                 tn=2.0, tf=6.0, seed=1, precision="bf16", world_size=1, use_graph=True, rank=None, group=None):
         self.net, self.N, self.B = net, int(N), int(batch_size)
-        self.tn, self.tf, self.seed = float(tn), float(tf), int(seed)
+        self.tn, self.tf = float(tn), float(tf)
         self.precision = {"fp32": _lib.FP32, "bf16": _lib.BF16}[precision]
-        self.world_size = world_size
+        self.world_size, self.group = int(world_size), group
+        self.rank = 0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.seed = int(seed) + 0x9E3779B1 * self.rank          # distinct Philox keys per rank
         self.device = next(net.parameters()).device
         self.rays_table = _lib.require_cuda(rays_table, "rays_table").float().contiguous()
         self.gt_table = _lib.require_cuda(gt_table, "gt_table").float().contiguous()
+        if self.rays_table.dim() != 2 or self.rays_table.shape[1] != 6 or self.gt_table.dim() != 2 or self.gt_table.shape[1] != 3:
+            raise ValueError("rays_table must be [n,6] and gt_table [n,3]")
+        if self.rays_table.shape[0] != self.gt_table.shape[0] or self.rays_table.shape[0] == 0:
+            raise ValueError(f"rays_table has {self.rays_table.shape[0]} rows, gt_table {self.gt_table.shape[0]}: "
+                             "the selection kernel gathers both with the same indices")
         self.flat_param = flatten_parameters(net)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.flat_param, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.flat_grad = attach_flat_grad(net)
         self.params = net.kernel_params()
         self.grads = [p.grad for p in self.params]
@@ -98,30 +120,36 @@ class Trainer:
         self._grad_ptrs = _lib.ptr_array(self.grads)
         self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
                             if self.precision == _lib.BF16 else None)
-        # (capturing the NCCL all-reduce itself hung on this stack -- torch 2.11, NCCL 2.28, two ranks -- so multi-rank
-        # steps replay two graphs with the collective launched eagerly in between)
+        # Multi-rank steps: NB200_GRAPH_ALLREDUCE=1 captures the NCCL all-reduce inside the step's graph (one replay
+        # per step); otherwise two graphs are replayed around an eagerly launched collective.
         self.use_graph = bool(use_graph) and self.precision == _lib.BF16 and self.N % 4 == 0 and self.N <= 1024
-        self._graph, self.graph_error = None, None
+        self.graph_allreduce = os.environ.get("NB200_GRAPH_ALLREDUCE", "0") == "1"
+        self._graphs, self.graph_error = {}, None
         self.launches = 0
         self.part_events = []
         self.last_loss = None
 
-    def _enqueue_step(self, time_parts=False, part="all"):
+    # ------------------------------------------------------------------------------------------ one step
+    def _enqueue_step(self, time_parts=False, part="all", select=True, sample=True):
         """Enqueue one training step on the current stream.  Everything that changes from step to step (Philox
         positions, Adam's step count, the learning rate) is read from the device-resident train state, so
-        the same sequence of launches can be captured once in a CUDA graph and replayed."""
+        the same sequence of launches can be captured once in a CUDA graph and replayed.
+        select=False: the batch (self._rays, self._gt) was supplied by the caller (host-side selection like
+        train.py:47-49); sample=False: the sample depths self._ts were supplied too (parity tests)."""
         lib = _lib.load()
         dev, B, N, M = self.device, self.B, self.N, self.B * self.N
         st = _lib.stream_ptr(dev)
         state = _lib.ptr(self._state)
         if part == "update":
             return self._enqueue_update(lib, state, st)
-        # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
         rays, gt, ts = self._rays, self._gt, self._ts
-        _lib.check(lib.nb200_select_rays_state(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
-                                               self.seed ^ 0x5E1EC7, state, B, _lib.ptr(rays), _lib.ptr(gt), None, st),
-                   "nb200_select_rays_state")
-        if N % 4 == 0 and N <= 1024:
+        if select:   # ray selection with replacement on the device (rg.select + train_imgs[ray_ids], train.py:47-49)
+            _lib.check(lib.nb200_select_rays_state(_lib.ptr(self.rays_table), _lib.ptr(self.gt_table), self.rays_table.shape[0],
+                                                   self.seed ^ 0x5E1EC7, state, B, _lib.ptr(rays), _lib.ptr(gt), None, st),
+                       "nb200_select_rays_state")
+        if not sample:
+            pass
+        elif N % 4 == 0 and N <= 1024:
             _lib.check(lib.nb200_stratified_ts_state(self.seed, state, B, N, self.tn, self.tf, _lib.ptr(ts), st),
                        "nb200_stratified_ts_state")
         else:   # ragged N: host-side stream position (not graph-replayable; use_graph is off for such N)
@@ -158,9 +186,9 @@ class Trainer:
         if time_parts:
             ev[3].record()
             self.part_events.append(ev)
-        if part == "grads":      # multi-rank graph mode: the all-reduce is launched eagerly between the two graphs
+        if part == "grads":      # two-graph mode: the all-reduce is launched eagerly between the two graphs
             return
-        allreduce_mean_(self.flat_grad, self.world_size)
+        allreduce_mean_(self.flat_grad, self.world_size, self.group)
         self._enqueue_update(lib, state, st)
 
     def _enqueue_update(self, lib, state, st):
@@ -170,50 +198,69 @@ class Trainer:
                                              self.betas[1], self.eps, st), "nb200_adam_step_state")
         _lib.check(lib.nb200_train_state_advance(state, B, (M + 3) // 4, self.lr_decay, st), "nb200_train_state_advance")
 
-    def _capture(self):
+    def _capture(self, select):
         """Capture one step in CUDA graphs (after eager warm-up steps have set kernel attributes, cached the
-        tensor maps and initialised NCCL).  Single rank: one graph.  Several ranks: one graph up to the local
-        gradients and one for the optimizer update, with the NCCL all-reduce launched eagerly in between
-        (capturing the collective itself hung on this stack).  Falls back to eager launches on failure."""
-        try:
-            torch.cuda.synchronize(self.device)
-            if self.world_size == 1:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue_step()
-                self._graph = (g,)
-            else:
-                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga):
-                    self._enqueue_step(part="grads")
-                with torch.cuda.graph(gb):
-                    self._enqueue_step(part="update")
-                self._graph = (ga, gb)
-        except Exception as e:
-            self._graph, self.use_graph = None, False
-            self.graph_error = repr(e)
-            torch.cuda.synchronize(self.device)
-
-    def step(self, sync_loss=False, time_parts=False):
-        """One training step.  time_parts=True (eager launches only) records CUDA events around the MLP forward
-        and the MLP backward (delta chain + wgrad) in self.part_events for bench.py's roofline."""
-        if self.use_graph and not time_parts:
-            if self._graph is None and self.t >= 2:
-                self._capture()
-            if self._graph is not None:
-                self._graph[0].replay()
-                if len(self._graph) == 2:
-                    allreduce_mean_(self.flat_grad, self.world_size)
-                    self._graph[1].replay()
-            else:
-                self._enqueue_step()
+        tensor maps and initialised NCCL).  One graph per step; with several ranks the NCCL all-reduce is part of
+        it (graph_allreduce) or -- fallback -- two graphs are replayed around the eagerly launched collective.
+        Every rank takes the same branch: the choice depends only on configuration, never on a local exception."""
+        torch.cuda.synchronize(self.device)
+        if self.world_size == 1 or self.graph_allreduce:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._enqueue_step(select=select)
+            self._graphs[select] = (g,)
         else:
-            self._enqueue_step(time_parts)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._enqueue_step(part="grads", select=select)
+            with torch.cuda.graph(gb):
+                self._enqueue_step(part="update")
+            self._graphs[select] = (ga, gb)
+
+    @property
+    def launch_mode(self):
+        if not self._graphs:
+            return "eager launches"
+        g = next(iter(self._graphs.values()))
+        if len(g) == 1:
+            return "one CUDA-graph replay per step" + (" (NCCL all-reduce captured in the graph)" if self.world_size > 1 else "")
+        return "two CUDA graphs per step around the eagerly launched NCCL all-reduce"
+
+    def step(self, sync_loss=False, time_parts=False, rays=None, gt=None, ts=None):
+        """One training step.  By default the batch is selected on the device.  rays [B,6] / gt [B,3] given (any
+        device; pinned host tensors are copied asynchronously): the caller's batch is used instead, like
+        train.py:47-51 does with rg.select + `.cuda()`; `ts` [B,N] given as well: those sample depths instead of the
+        Philox jitter (parity tests; eager launches).  time_parts=True (eager launches only) records CUDA events
+        around the MLP forward and the MLP backward in self.part_events for bench.py's roofline."""
+        select = rays is None
+        if not select:
+            if gt is None or tuple(rays.shape) != (self.B, 6) or tuple(gt.shape) != (self.B, 3):
+                raise ValueError(f"rays must be [{self.B},6] and gt [{self.B},3]")
+            self._rays.copy_(rays, non_blocking=True)
+            self._gt.copy_(gt, non_blocking=True)
+        if ts is not None:
+            if tuple(ts.shape) != (self.B, self.N):
+                raise ValueError(f"ts must be [{self.B},{self.N}]")
+            self._ts.copy_(ts, non_blocking=True)
+        if self.use_graph and not time_parts and ts is None:
+            if select not in self._graphs and self.t >= 2:
+                self._capture(select)
+            g = self._graphs.get(select)
+            if g is not None:
+                g[0].replay()
+                if len(g) == 2:
+                    allreduce_mean_(self.flat_grad, self.world_size, self.group)
+                    g[1].replay()
+            else:
+                self._enqueue_step(select=select)
+        else:
+            self._enqueue_step(time_parts, select=select, sample=ts is None)
         self.t += 1
         self._offset += (self.B * self.N + 3) // 4
         self.lr *= self.lr_decay
         self._bump_versions()
-        self.launches += 14 if self.precision == _lib.BF16 else 65   # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, dgrad, wgrad(+heads), unpad, adam, state (+ 2 memsets)
+        # select, ts, pack x2, fwd, comp fwd, mse, comp bwd, bwd kernels, unpad, adam, state (+ memsets)
+        self.launches += (14 if self.precision == _lib.BF16 else 65) - (0 if select else 1) - (0 if ts is None else 1)
         self.last_loss = self._loss
         return float(self._loss) if sync_loss else self._loss.clone()
 

@@ -51,6 +51,10 @@ def _worker(rank, world, port, out):
     from nerf_simple_b200.engine import gather_shards
     full = gather_shards(local, n, rank, world)
     ok &= bool(full.shape == (n, 4) and torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32)))
+    n = 1000                                                      # equal bands: the single-buffer collective
+    b, e = shard_range(n, rank, world)
+    full = gather_shards(torch.arange(b, e, dtype=torch.float32)[:, None].repeat(1, 4), n, rank, world)
+    ok &= bool(full.shape == (n, 4) and torch.equal(full[:, 3], torch.arange(n, dtype=torch.float32)))
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

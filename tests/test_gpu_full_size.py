@@ -1,0 +1,233 @@
+"""GPU parity at BASELINE sizes and through the reference's own host loops:
+  * one training step at 4096 rays x 64 samples (configs[2]) against the reference's autograd (golden case F),
+    through render_nerf + autograd AND through the device-resident Trainer (the path bench.py times);
+  * render_image / render_poses pixels against the reference's own chunk loops (golden case G)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# north star: fp32/tf32 max abs err <= 1e-4, bf16 <= 1e-2; gradients "within matching tolerance"
+ABS = {"fp32": 1e-4, "bf16": 1e-2}
+REL = {"fp32": 2e-3, "bf16": 5e-2}       # of each tensor's max |gradient|
+
+
+def maxabs(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+
+
+def _net(golden_weights, extra=None):
+    from nerf_simple_b200.nets import Nerf
+    n = Nerf().cuda()
+    sd = {k: torch.from_numpy(v.copy()) for k, v in golden_weights.items()}
+    if extra:
+        for k, d in extra.items():
+            sd[k] = sd[k] + torch.as_tensor(d)
+    n.load_state_dict(sd, strict=True)
+    return n
+
+
+@pytest.fixture(params=["fp32", "bf16"])
+def precision(request):
+    from nerf_simple_b200 import config
+    config.set_precision(request.param)
+    config.set_sampler("reference")
+    yield request.param
+    config.set_precision("bf16")
+
+
+def _check_grads(named_grads, g, precision, report):
+    worst_abs = worst_rel = 0.0
+    for k, grad in named_grads:
+        ref = g["grad." + k]
+        scale = max(1e-6, float(np.max(np.abs(ref))))
+        err = maxabs(grad, ref)
+        worst_abs, worst_rel = max(worst_abs, err), max(worst_rel, err / scale)
+        assert err <= ABS[precision], (k, err)                 # the north star's absolute number
+        assert err <= REL[precision] * scale, (k, err, scale)  # and relative to the tensor, so a wrong head gradient shows
+    report.append((worst_abs, worst_rel))
+
+
+def test_train_step_4096x64_autograd_path(golden_weights, precision):
+    """train.py:51-54 at configs[2] size: render_nerf -> MSELoss -> backward, against the reference's autograd."""
+    from nerf_simple_b200.rendering import render_nerf
+    g = load_golden("case_train_b4096_n64.npz")
+    net = _net(golden_weights)
+    torch.manual_seed(int(g["u_seed"]))                        # render_nerf draws torch.rand(4096,64) like :28
+    rgb, disp, alpha, acc, w = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 64)
+    loss = torch.nn.MSELoss()(rgb, torch.from_numpy(g["gt"]).cuda())
+    loss.backward()
+    assert maxabs(rgb, g["rgb"]) <= ABS[precision]
+    assert maxabs(acc, g["acc"]) <= ABS[precision]
+    assert abs(loss.item() - float(g["loss"])) <= (1e-5 if precision == "fp32" else 1e-3)
+    rep = []
+    _check_grads([(k, p.grad) for k, p in net.named_parameters()], g, precision, rep)
+    print(f"4096x64 autograd path [{precision}]: worst abs grad err {rep[0][0]:.3e}, worst rel {rep[0][1]:.3e}")
+
+
+def test_trainer_one_step_vs_reference(golden_weights, precision):
+    """The device-resident Trainer (what bench.py times) fed the golden batch and sample depths: loss, flat
+    gradient and the post-Adam parameters against the reference's autograd / torch.optim.Adam semantics."""
+    from nerf_simple_b200.trainer import Trainer
+    g = load_golden("case_train_b4096_n64.npz")
+    net = _net(golden_weights)
+    rays, gt = torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["gt"]).cuda()
+    torch.manual_seed(int(g["u_seed"]))
+    ts = torch.from_numpy(O.stratified_ts(torch.rand(4096, 64).numpy(), 64)).cuda()
+    tr = Trainer(net, rays, gt, N=64, batch_size=4096, precision=precision)
+    p0 = tr.flat_param.clone()
+    loss = tr.step(sync_loss=True, rays=rays, gt=gt, ts=ts)
+    assert abs(loss - float(g["loss"])) <= (1e-5 if precision == "fp32" else 1e-3)
+    assert maxabs(tr._rgb, g["rgb"]) <= ABS[precision]
+    rep = []
+    _check_grads([(k, p.grad) for k, p in net.named_parameters()], g, precision, rep)
+    # Adam (train.py:43,55), first step, applied to the gradient the device produced
+    want, _, _ = O.adam_step(p0.cpu().numpy(), tr.flat_grad.cpu().numpy(), 0.0, 0.0, 1)
+    assert maxabs(tr.flat_param, want) <= 1e-6
+    # and the 24 nn.Parameters really are the updated values (views of the flat buffer)
+    moved = sum(float((p.detach().cpu() - torch.from_numpy(golden_weights[k])).abs().max()) > 1e-5 for k, p in net.named_parameters())
+    assert moved == 24
+    # a second step with the same batch through the SAME entry point, replaying nothing stale: loss must drop
+    loss2 = tr.step(sync_loss=True, rays=rays, gt=gt, ts=ts)
+    assert loss2 < loss
+
+
+def test_trainer_graph_step_equals_supplied_batch_step(golden_weights):
+    """The graph-replayed step selects rays and draws jitter on the device.  Read the batch it used back and feed
+    it to the oracle: same loss and gradient within the bf16 tolerance (pins the path bench.py times end to end)."""
+    from nerf_simple_b200.trainer import Trainer
+    g = load_golden("case_train_b4096_n64.npz")
+    net = _net(golden_weights)
+    table = torch.from_numpy(g["rays"]).cuda()
+    gt_table = torch.from_numpy(g["gt"]).cuda()
+    tr = Trainer(net, table, gt_table, N=64, batch_size=512, precision="bf16")
+    for _ in range(3):
+        tr.step()                                              # two eager steps, then the captured graph
+    assert tr.launch_mode.startswith("one CUDA-graph")
+    P = {k: p.detach().cpu().numpy().copy() for k, p in net.named_parameters()}    # weights the NEXT step will use
+    loss = tr.step(sync_loss=True)
+    rays, gt, ts = tr._rays.cpu().numpy(), tr._gt.cpu().numpy(), tr._ts.cpu().numpy()
+    assert np.isin(rays[:, 3], g["rays"][:, 3]).all()          # rows of the table
+    loss_ref, grads_ref, rgb_ref = O.train_step_grads(rays, P, 64, None, gt, ts=ts)
+    assert abs(loss - loss_ref) <= 1e-3 and maxabs(tr._rgb, rgb_ref) <= 1e-2
+    for k, p in net.named_parameters():
+        scale = max(1e-6, float(np.abs(grads_ref[k]).max()))
+        err = maxabs(p.grad, grads_ref[k])
+        assert err <= 1e-2 and err <= 6e-2 * scale, (k, err, scale)      # 512 rays: less averaging than 4096
+
+
+def _chunk_net(golden_weights, g):
+    return _net(golden_weights, {"color_fc.2.bias": g["bias_shift"][:3], "sigma_fc.0.bias": g["bias_shift"][3:4]})
+
+
+def _psnr(a, b):
+    return float(-10 * np.log10(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2)))
+
+
+def test_render_image_pixels_vs_reference(golden_weights, precision):
+    """render_image (utils/rendering.py:88-113): same chunks, same per-chunk torch.rand stream, N=128, clip."""
+    from nerf_simple_b200.rendering import render_image
+    g = load_golden("case_chunk_loops.npz")
+    net = _chunk_net(golden_weights, g)
+    H, W = int(g["cam"][0]), int(g["cam"][1])
+
+    class RG:
+        samples = {"val": [{"img": g["gt2"]} for _ in range(4)]}
+        rays_dataset = {"val": torch.from_numpy(g["rays"])}
+    torch.manual_seed(int(g["image_seed"]))
+    rgb, depth, gt = render_image(net, RG, batch_size=100, im_idx=2, im_set="val")
+    assert rgb.shape == (1, H, W, 3) and depth.shape == (1, H, W, 1) and not rgb.is_cuda
+    assert maxabs(rgb, g["image_rgb"]) <= ABS[precision]
+    assert float(np.max(np.abs(depth.numpy() - g["image_depth"]) / g["image_depth"])) <= 10 * ABS[precision]
+    assert np.array_equal(np.asarray(gt), g["image_gt"])
+    # clip of :103 was exercised on both sides
+    assert float(rgb.max()) == 1.0 and float(rgb.min()) == 0.0
+    # rendered-image PSNR against the ground truth: ours vs the reference's, delta <= 0.1 dB
+    assert abs(_psnr(rgb.numpy(), g["image_gt"]) - _psnr(g["image_rgb"], g["image_gt"])) <= 0.1
+
+
+def test_render_poses_frames_vs_reference(golden_weights, precision, tmp_path, monkeypatch):
+    """render_poses (utils/rendering.py:116-160): the uint8 BGR frames handed to cv2.VideoWriter."""
+    import cv2
+    from nerf_simple_b200.rendering import render_poses
+    g = load_golden("case_chunk_loops.npz")
+    net = _chunk_net(golden_weights, g)
+    H, W, f = int(g["cam"][0]), int(g["cam"][1]), float(g["cam"][2])
+    written, args = [], []
+
+    class Recorder:
+        def __init__(self, *a):
+            args.append(a)
+        def write(self, fr):
+            written.append(np.array(fr))
+        def release(self):
+            pass
+    monkeypatch.setattr(cv2, "VideoWriter", Recorder)
+    torch.manual_seed(int(g["poses_seed"]))
+    frames = render_poses(net, [torch.from_numpy(p) for p in g["poses"][:2]], [H, W, f], 80, savepath=str(tmp_path))
+    assert len(written) == 2 and written[0].dtype == np.uint8 and written[0].shape == (H, W, 3)
+    assert args[0][2] == 15 and args[0][3] == (H, W)                       # fps and the (H,W) size of :156
+    tol = 1 if precision == "fp32" else 3                                  # 1e-2 * 255 = 2.55 levels
+    for a, b, fr in zip(written, g["frames_bgr_u8"], frames):
+        assert int(np.max(np.abs(a.astype(int) - b.astype(int)))) <= tol
+        # the uint8 frame is exactly the float frame clipped, swapped and truncated (:158-159)
+        assert np.array_equal(a, (fr[..., ::-1] * np.float32(255)).astype(np.uint8))
+
+
+def test_frame_to_u8_exact():
+    """nb200_frame_to_u8 == (cv2.cvtColor(clip(frame), RGB2BGR) * 255).astype(uint8), bit for bit, any pixel count."""
+    from nerf_simple_b200 import ops
+    torch.manual_seed(0)
+    for n in (1, 3, 4, 1001, 640000):
+        x = (torch.rand(n, 3, device="cuda") * 1.4 - 0.2)
+        x[:: 7] = 1.0
+        x[3:: 11] = 0.0
+        ref = (x.clamp(0, 1).cpu().numpy() * 255).astype(np.uint8)
+        assert np.array_equal(ops.frame_to_u8(x, bgr=False).cpu().numpy(), ref)
+        assert np.array_equal(ops.frame_to_u8(x, bgr=True).cpu().numpy(), ref[:, ::-1])
+    assert ops.frame_to_u8(torch.zeros(0, 3, device="cuda")).shape == (0, 3)
+
+
+def test_two_nets_on_two_streams_do_not_share_biases(golden_weights):
+    """Concurrent nets (coarse + fine on their own streams) each keep their biases: the constant-bank copy of the
+    fp32 tail is per packed buffer."""
+    g = load_golden("case_train_b64_n64.npz")
+    q = torch.from_numpy(g["query"]).cuda().repeat(64, 1)
+    a = _net(golden_weights)
+    b = _net(golden_weights, {"color_fc.2.bias": np.array([10.0, 20.0, 30.0], np.float32), "sigma_fc.0.bias": np.array([5.0], np.float32)})
+    for n in (a, b):
+        n.precision = "bf16"
+    with torch.no_grad():
+        ref_a, ref_b = a(q).clone(), b(q).clone()
+        torch.cuda.synchronize()
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = []
+        for it in range(20):
+            with torch.cuda.stream(sa):
+                oa = a(q)
+            with torch.cuda.stream(sb):
+                ob = b(q)
+            outs.append((oa, ob))
+        torch.cuda.synchronize()
+    for oa, ob in outs:
+        assert torch.equal(oa, ref_a) and torch.equal(ob, ref_b)
+    assert float((ref_b[:, 0] - ref_a[:, 0]).mean()) == pytest.approx(10.0, abs=1e-3)
+
+
+def test_invalidate_packed_after_data_write(golden_weights):
+    """Writes through `.data` bypass the version counters the packed-weight cache is keyed on: invalidate_packed()."""
+    net = _net(golden_weights)
+    net.precision = "bf16"
+    q = torch.from_numpy(load_golden("case_train_b64_n64.npz")["query"][:256]).cuda()
+    with torch.no_grad():
+        y0 = net(q).clone()
+        net.color_fc[2].bias.data.add_(1.0)
+        net.invalidate_packed()
+        y1 = net(q)
+    assert float((y1[:, :3] - y0[:, :3]).mean()) == pytest.approx(1.0, abs=1e-3)

@@ -1,0 +1,26 @@
+"""Two-rank NCCL test of the north star's multi-GPU split: ray bands of one frame + one all_gather, and
+data-parallel training with one all-reduce per step.  Needs two GPUs (`gpurun --gpus 2`); skipped on a one-GPU box,
+where tests/test_distributed_cpu.py (gloo, world size 2) covers the host logic."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("graph_allreduce", ["0", "1"])
+def test_two_rank_sharded_render_and_dp_training(graph_allreduce):
+    env = dict(os.environ, NB200_GRAPH_ALLREDUCE=graph_allreduce)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "scripts", "check_multirank.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["all_ranks_ok"] and res["sharded_frame_bit_identical"] and res["replicas_identical_after_30_steps"]
+    assert ("captured in the graph" in res["launch_mode"]) == (graph_allreduce == "1"), res["launch_mode"]

@@ -228,8 +228,8 @@ def test_trainer_graph_replay_matches_eager():
         losses = [tr.step(sync_loss=True) for _ in range(25)]
         state = tr._state.cpu()
         runs[use_graph] = (losses, state, tr)
-    assert runs[True][2]._graph is not None, runs[True][2].graph_error          # the capture succeeded and is in use
-    assert runs[False][2]._graph is None
+    assert runs[True][2]._graphs and runs[True][2].launch_mode.startswith("one CUDA-graph")    # the capture succeeded and is in use
+    assert not runs[False][2]._graphs
     # device-resident state after 25 steps: select offset, sampler offset (quads), step count, lr
     for losses, state, tr in runs.values():
         q = state[:24].view(torch.int64)
