@@ -202,6 +202,19 @@ int nb200_stratified_ts_state(uint64_t seed, const void* state, int64_t B, int N
 int nb200_adam_step_state(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                           const void* state, float beta1, float beta2, float eps, nb200_stream_t stream);
 
+/* Data-parallel training (new functionality; the reference is single-GPU): the gradient all-reduce FUSED
+ * into the Adam update over NVLink peer memory.  Replaces an NCCL all-reduce of the flat gradient followed by
+ * nb200_adam_step_state: every rank's kernel reads the flat gradients of all `world` ranks (peer_grads: HOST array of
+ * `world` DEVICE pointers, index = rank, the caller's own buffer included; peers mapped through CUDA IPC), averages
+ * them in rank order and applies Adam to its own replica, so replicas stay bit-identical.  peer_flags: HOST array of
+ * `world` DEVICE pointers to each rank's zero-initialised flag block of NB200_P2P_FLAG_WORDS uint32 (remote ranks write
+ * arrival / completion epochs there; the epoch is the optimizer step count of `state`).  Every rank must enqueue the
+ * call once per step.  n (floats) must be a multiple of 4; world <= 8 (one NVSwitch domain). */
+#define NB200_P2P_FLAG_WORDS 32
+int nb200_adam_allreduce_p2p(float* param, const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
+                             float* exp_avg, float* exp_avg_sq, int64_t n, const void* state, float beta1, float beta2,
+                             float eps, nb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ OK = 0
 FP32, BF16 = 0, 1
 IN_POINTS, IN_RAYS = 0, 1
 TRAIN_STATE_BYTES = 32     # NB200_TRAIN_STATE_BYTES
+P2P_FLAG_WORDS = 32        # NB200_P2P_FLAG_WORDS
 
 # every symbol include/nerf_b200.h declares: name -> (restype, argtypes)
 _p, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -48,6 +49,7 @@ SYMBOLS = {
     "nb200_select_rays_state": (_i, [_p, _p, _i64, _u64, _p, _i64, _p, _p, _p, _p]),
     "nb200_stratified_ts_state": (_i, [_u64, _p, _i64, _i, _f, _f, _p, _p]),
     "nb200_adam_step_state": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _p]),
+    "nb200_adam_allreduce_p2p": (_i, [_p, _p, _p, _i, _i, _p, _p, _i64, _p, _f, _f, _f, _p]),
     "nb200_frame_to_u8": (_i, [_p, _i64, _i, _p, _p]),
     "nb200_sample_pdf_merge": (_i, [_p, _p, _p, _i, _u64, _u64, _i64, _i, _i, _p, _p]),
 }

@@ -216,6 +216,105 @@ __global__ void __launch_bounds__(256) adam_flat_state_kernel(float* __restrict_
   }
 }
 
+// ------------------------------------------------- gradient all-reduce fused into Adam (NVLink peer memory)
+// Data-parallel training: instead of an NCCL all-reduce followed by the optimizer kernel, every rank's
+// Adam kernel reads the flat gradient of ALL ranks straight out of their HBM over NVLink / NVSwitch (the buffers
+// are mapped into each process through CUDA IPC), sums them in rank order (identical on every rank, so the
+// replicas stay bit-identical), divides by the world size and applies the update to its own replica.  2.38 MB per
+// peer per step: a few microseconds of NVLink time, no separate collective, and the whole step stays ONE CUDA graph.
+//   entry : block 0 tells every peer "my gradients of step `epoch` are complete" (release, system scope); every block
+//           waits until all peers said so (acquire, system scope)
+//   exit  : the last block to finish tells every peer "I am done reading yours" and waits for the same from them, so
+//           that stream order protects this rank's gradient buffer from its own next step
+// flags of rank r (device memory of r, written remotely): [0, kMaxPeers) ready epochs, [kMaxPeers, 2 kMaxPeers) done
+// epochs, [2 kMaxPeers] block counter.
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  const float* grad[kMaxPeers];
+  uint32_t* flags[kMaxPeers];
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {   // never served from a stale (non-coherent) L1 line
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin: a rank that never arrives must surface as a launch error, not as a hung GPU.
+__device__ __forceinline__ void wait_epoch(const uint32_t* flag, uint32_t epoch, int tag) {
+  uint64_t t0 = 0;
+  uint32_t it = 0;
+  while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+    if ((++it & 0x3FFu) == 0u) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) {
+        printf("nb200: peer flag wait timed out (block %d thread %d tag %d epoch %u)\n", blockIdx.x, threadIdx.x, tag, epoch);
+        __trap();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_allreduce_p2p_kernel(float* __restrict__ p, PeerPtrs peers, int rank, int world,
+                                                                 float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                                 const TrainState* __restrict__ st, float beta1, float beta2, float eps) {
+  const uint32_t epoch = (uint32_t)(st->step + 1);
+  uint32_t* mine = peers.flags[rank];
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();                                   // this rank's gradient writes (earlier kernels) before the flag
+    st_release_sys(peers.flags[threadIdx.x] + rank, epoch);   // flags[r][ready + me] = epoch
+  }
+  if ((int)threadIdx.x < world) wait_epoch(mine + threadIdx.x, epoch, 1);
+  __syncthreads();
+  const float t = (float)(st->step + 1);
+  const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  const float step_size = st->lr / bc1, inv_world = 1.f / (float)world;
+  const int64_t n4 = n >> 2;                                  // the flat buffers are padded to multiples of 4 floats
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {                     // rank order: the same sum on every rank
+      if (r < world) {
+        const float4 x = ld_relaxed_sys_f4(peers.grad[r] + 4 * q);
+        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+      }
+    }
+    float4 pp = reinterpret_cast<float4*>(p)[q], mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; float* ga = &g.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gi = ga[k] * inv_world;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gi;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gi * gi;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(p)[q] = pp; reinterpret_cast<float4*>(m)[q] = mm; reinterpret_cast<float4*>(v)[q] = vv;
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(mine + 2 * kMaxPeers, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    if ((int)threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(peers.flags[threadIdx.x] + kMaxPeers + rank, epoch);    // "I am done reading your gradients"
+      wait_epoch(mine + kMaxPeers + threadIdx.x, epoch, 2);                  // everyone is done reading mine
+    }
+    if (threadIdx.x == 0) mine[2 * kMaxPeers] = 0u;
+  }
+}
+
 __global__ void train_state_advance_kernel(TrainState* st, uint64_t select_inc, uint64_t sample_inc, float lr_decay) {
   st->select_offset += select_inc;
   st->sample_offset += sample_inc;
@@ -403,6 +502,30 @@ int nb200_adam_step_state(float* param, const float* grad, float* exp_avg, float
   adam_flat_state_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, as_stream(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, reinterpret_cast<const TrainState*>(state), beta1, beta2, eps);
   NB_LAUNCH_CHECK("adam_flat_state_kernel");
+  return NB200_OK;
+}
+
+
+int nb200_adam_allreduce_p2p(float* param, const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
+                             float* exp_avg, float* exp_avg_sq, int64_t n, const void* state, float beta1, float beta2,
+                             float eps, nb200_stream_t stream) {
+  using namespace nb200;
+  if (!param || !peer_grads || !peer_flags || !exp_avg || !exp_avg_sq || !state || n < 0) return NB200_ERR_ARG;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return NB200_ERR_UNSUPPORTED;
+  if ((n & 3) || (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15)) return NB200_ERR_ARG;
+  PeerPtrs pp;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    pp.grad[r] = r < world ? peer_grads[r] : nullptr;
+    pp.flags[r] = r < world ? peer_flags[r] : nullptr;
+    if (r < world && (!pp.grad[r] || !pp.flags[r] || ((uintptr_t)pp.grad[r] & 15))) return NB200_ERR_ARG;
+  }
+  if (n == 0) return NB200_OK;
+  // every block spins on the peers at entry: keep the grid within one wave so that no block waits for a slot
+  const int64_t blocks = ceil_div64(n >> 2, 256);
+  const int grid = (int)(blocks < (int64_t)sm_count() * 4 ? blocks : (int64_t)sm_count() * 4);
+  adam_allreduce_p2p_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, pp, rank, world, exp_avg, exp_avg_sq, n,
+                                                                reinterpret_cast<const TrainState*>(state), beta1, beta2, eps);
+  NB_LAUNCH_CHECK("adam_allreduce_p2p_kernel");
   return NB200_OK;
 }
 

@@ -8,9 +8,9 @@ the ray table and the ground-truth colours live on the device, a step is
 and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
 needs exactly one NCCL all-reduce of 595,844 floats per step.  Everything that varies
 from step to step lives in a 32-byte device-resident state, so after two eager warm-up steps the
-whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks the NCCL
-all-reduce is captured inside the graph, or -- NB200_GRAPH_ALLREDUCE=0 -- two graphs are replayed
-around the eagerly launched collective).  The batch can also be handed in by the caller
+whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks the gradient
+all-reduce is fused into the Adam kernel over NVLink peer memory, or -- NB200_P2P_ALLREDUCE=0 -- two
+graphs are replayed around an eagerly launched NCCL all-reduce).  The batch can also be handed in by the caller
 (`step(rays=, gt=)`, pinned host tensors copied asynchronously), which is train.py's own flow.
 """
 from __future__ import annotations
@@ -42,6 +42,29 @@ def attach_flat_grad(net, device=None):
     for p, v in zip(params, flat_views(flat, shapes)):
         p.grad = v
     return flat
+
+
+def share_peer_buffers(local, group=None):
+    """Map the CUDA tensor `local` of every rank of `group` into this process (CUDA IPC through torch's own storage
+    sharing, the mechanism torch.multiprocessing uses) and return the list of `world` tensors, index = rank, own
+    tensor included.  Peer access between the devices is switched on by a first cross-device copy.  Raises when the
+    ranks are not on one node / have no peer access -- callers fall back to NCCL."""
+    import torch.distributed as dist
+    from torch.multiprocessing.reductions import reduce_tensor
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    descs = [None] * world
+    dist.all_gather_object(descs, reduce_tensor(local), group=group)      # (rebuild function, IPC handle + layout)
+    out = []
+    for r, (rebuild, args) in enumerate(descs):
+        if r == rank:
+            out.append(local)
+            continue
+        t = rebuild(*args)                     # cudaIpcOpenMemHandle: the peer's allocation in this address space
+        if t.device.index != local.device.index and not torch.cuda.can_device_access_peer(local.device.index, t.device.index):
+            raise RuntimeError(f"no peer access between cuda:{local.device.index} and cuda:{t.device.index}")
+        t.view(-1)[:1].to(local.device)       # first cross-device copy: torch enables peer access for the pair
+        out.append(t)
+    return out
 
 
 def allreduce_mean_(flat_grad, world_size, group=None):
@@ -120,14 +143,38 @@ class Trainer:
         self._grad_ptrs = _lib.ptr_array(self.grads)
         self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
                             if self.precision == _lib.BF16 else None)
-        # Multi-rank steps: NB200_GRAPH_ALLREDUCE=1 captures the NCCL all-reduce inside the step's graph (one replay
-        # per step); otherwise two graphs are replayed around an eagerly launched collective.
+        # Multi-rank steps: the gradient all-reduce is fused into the Adam kernel over NVLink peer memory
+        # (nb200_adam_allreduce_p2p), so a step stays ONE graph replay.  NB200_P2P_ALLREDUCE=0, or ranks without peer
+        # access, use NCCL instead: two graphs are replayed around the eagerly launched collective (capturing the NCCL
+        # all-reduce itself inside torch.cuda.graph hung on this stack -- torch 2.11, NCCL 2.28.9 -- in every capture mode).
         self.use_graph = bool(use_graph) and self.precision == _lib.BF16 and self.N % 4 == 0 and self.N <= 1024
-        self.graph_allreduce = os.environ.get("NB200_GRAPH_ALLREDUCE", "0") == "1"
+        self._p2p, self.p2p_error = None, None
+        if self.world_size > 1 and os.environ.get("NB200_P2P_ALLREDUCE", "1") == "1" and self.flat_grad.is_cuda:
+            self._setup_p2p()
         self._graphs, self.graph_error = {}, None
         self.launches = 0
         self.part_events = []
         self.last_loss = None
+
+    def _setup_p2p(self):
+        """Exchange the flat gradient buffers and the flag blocks with the other ranks (same node, <= 8 ranks)."""
+        import torch.distributed as dist
+        ok = torch.ones(1, device=self.device)
+        try:
+            if self.world_size > 8:
+                raise RuntimeError("more than 8 ranks")
+            self._p2p_flags = torch.zeros(_lib.P2P_FLAG_WORDS, dtype=torch.int32, device=self.device)
+            grads = share_peer_buffers(self.flat_grad, self.group)
+            flags = share_peer_buffers(self._p2p_flags, self.group)
+            self._p2p = (grads, flags, _lib.ptr_array(grads), _lib.ptr_array(flags))
+        except Exception as e:      # noqa: BLE001 -- any failure means "use NCCL"; recorded, and agreed on by all ranks below
+            self.p2p_error = repr(e)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank takes the same path
+        if float(ok) == 0.0:
+            self._p2p = None
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
 
     # ------------------------------------------------------------------------------------------ one step
     def _enqueue_step(self, time_parts=False, part="all", select=True, sample=True):
@@ -188,23 +235,29 @@ class Trainer:
             self.part_events.append(ev)
         if part == "grads":      # two-graph mode: the all-reduce is launched eagerly between the two graphs
             return
-        allreduce_mean_(self.flat_grad, self.world_size, self.group)
+        if self._p2p is None:
+            allreduce_mean_(self.flat_grad, self.world_size, self.group)
         self._enqueue_update(lib, state, st)
 
     def _enqueue_update(self, lib, state, st):
         B, M = self.B, self.B * self.N
-        _lib.check(lib.nb200_adam_step_state(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
-                                             _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state, self.betas[0],
-                                             self.betas[1], self.eps, st), "nb200_adam_step_state")
+        if self._p2p is not None:   # all-reduce fused into Adam: peers' gradients are read over NVLink inside the kernel
+            _lib.check(lib.nb200_adam_allreduce_p2p(_lib.ptr(self.flat_param), self._p2p[2], self._p2p[3], self.rank, self.world_size,
+                                                    _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state,
+                                                    self.betas[0], self.betas[1], self.eps, st), "nb200_adam_allreduce_p2p")
+        else:
+            _lib.check(lib.nb200_adam_step_state(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                                 _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state, self.betas[0],
+                                                 self.betas[1], self.eps, st), "nb200_adam_step_state")
         _lib.check(lib.nb200_train_state_advance(state, B, (M + 3) // 4, self.lr_decay, st), "nb200_train_state_advance")
 
     def _capture(self, select):
         """Capture one step in CUDA graphs (after eager warm-up steps have set kernel attributes, cached the
-        tensor maps and initialised NCCL).  One graph per step; with several ranks the NCCL all-reduce is part of
-        it (graph_allreduce) or -- fallback -- two graphs are replayed around the eagerly launched collective.
-        Every rank takes the same branch: the choice depends only on configuration, never on a local exception."""
+        tensor maps and initialised NCCL).  One graph per step; with several ranks the all-reduce is fused into the
+        Adam kernel (peer memory) or -- fallback -- two graphs are replayed around the eagerly launched NCCL collective.
+        Every rank takes the same branch: _setup_p2p agreed on it with a collective, never a local exception."""
         torch.cuda.synchronize(self.device)
-        if self.world_size == 1 or self.graph_allreduce:
+        if self.world_size == 1 or self._p2p is not None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._enqueue_step(select=select)
@@ -223,7 +276,7 @@ class Trainer:
             return "eager launches"
         g = next(iter(self._graphs.values()))
         if len(g) == 1:
-            return "one CUDA-graph replay per step" + (" (NCCL all-reduce captured in the graph)" if self.world_size > 1 else "")
+            return "one CUDA-graph replay per step" + (" (gradient all-reduce fused into the Adam kernel over NVLink peer memory)" if self.world_size > 1 else "")
         return "two CUDA graphs per step around the eagerly launched NCCL all-reduce"
 
     def step(self, sync_loss=False, time_parts=False, rays=None, gt=None, ts=None):

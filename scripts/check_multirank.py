@@ -3,7 +3,7 @@
   1. a ray-sharded frame assembled by one all_gather is BIT-IDENTICAL to the frame one GPU renders (SURVEY 8e);
   2. a data-parallel Trainer: ranks draw different rays, replicas start identical (broadcast) and stay identical,
      the all-reduced gradient is the mean of the per-rank gradients, the loss falls; checked in the launch mode
-     given by NB200_GRAPH_ALLREDUCE (1: the collective is captured in the step's CUDA graph, 0: two graphs).
+     given by NB200_P2P_ALLREDUCE (1: all-reduce fused into the Adam kernel over peer memory, one graph; 0: NCCL between two graphs).
 Prints one JSON line on rank 0 and exits non-zero on any failed check."""
 import json
 import os
@@ -60,6 +60,7 @@ ref = tr.flat_param.clone()
 dist.broadcast(ref, 0)
 res["replicas_identical_after_30_steps"] = bool(torch.equal(tr.flat_param, ref))
 res["launch_mode"] = tr.launch_mode
+res["p2p_error"] = tr.p2p_error
 res["loss_first_last"] = [losses[0], losses[-1]]
 # the all-reduced gradient of one more step == mean of the local gradients (recomputed eagerly without the collective)
 tr.use_graph = False

@@ -15,7 +15,6 @@ for st in $stages; do
     ncu_launch)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_train.csv python bench.py --workload train --steps 3 --warmup 3 > $out/${tag}_ncu_train.log 2>&1
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_render.csv python bench.py --workload render --steps 3 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_render.log 2>&1 ;;
-    probe)  timeout 900 python scripts/nccl_graph_probe.py 2 > $out/${tag}_nccl_probe.log 2>&1; cat $out/${tag}_nccl_probe.log ;;
     multirank) timeout 900 python -m pytest tests/test_gpu_multirank.py -x -q -s > $out/${tag}_multirank.log 2>&1; echo "multirank rc=$?"; tail -15 $out/${tag}_multirank.log ;;
     bench2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $out/${tag}_bench2.json 2> $out/${tag}_bench2.err; echo "bench2 rc=$?"; tail -c 3000 $out/${tag}_bench2.json; tail -5 $out/${tag}_bench2.err ;;
     bench8) for n in 4 8; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 20 --warmup 5 > $out/${tag}_bench$n.json 2> $out/${tag}_bench$n.err; echo "bench$n rc=$?"; tail -c 2500 $out/${tag}_bench$n.json; done ;;

@@ -33,7 +33,7 @@ def test_reference_train_and_test_cli_unchanged(tmp_path):
     sums = dict(reversed(ln.split()) for ln in open(os.path.join(REF, "SHA256SUMS")).read().splitlines())
     for name in ("train.py", "test.py", "utils/rendering.py", "utils/nets.py"):
         assert hashlib.sha256(open(os.path.join(REF, name), "rb").read()).hexdigest() == sums[name]
-    data = write_dataset(str(tmp_path / "lego"), H=24, W=24, n_train=3, n_val=2, n_test=2)
+    data = write_dataset(str(tmp_path / "lego"), H=24, W=24, n_train=3, n_val=3, n_test=3)   # load_data takes num_imgs of EVERY split (utils/dataload.py:55-61)
     models, results = str(tmp_path / "models"), str(tmp_path / "results")
     cfg = yaml.safe_load(open(os.path.join(REF, "configs", "lego.yaml")))      # the reference's own config, paths/sizes shrunk
     cfg.update(datapath=data, savepath=models, exp_name="cli", num_iters=120, ckpt_model=100, ckpt_loss=10, ckpt_images=100,
