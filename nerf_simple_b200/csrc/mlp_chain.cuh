@@ -387,7 +387,7 @@ __device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint
 // thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
 // (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, uint8_t* gsave,
+__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, uint32_t& mflags,
                                            float& sigma) {
   const float* b = c.cf + bias_off + col0;
   const float* ws = c.cf + kF32WSig + col0;
@@ -408,6 +408,10 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
     if (kRelu) {
       w0 = pack_bf16x2_relu(x[0], x[1]); w1 = pack_bf16x2_relu(x[2], x[3]);
       w2 = pack_bf16x2_relu(x[4], x[5]); w3 = pack_bf16x2_relu(x[6], x[7]);
+      if (kSave) {  // ReLU bit mask of the saved (bf16) activation, read by the delta chain
+        add_pair_flags(mflags, w0, 4 * j); add_pair_flags(mflags, w1, 4 * j + 1);
+        add_pair_flags(mflags, w2, 4 * j + 2); add_pair_flags(mflags, w3, 4 * j + 3);
+      }
     } else {
       w0 = pack_bf16x2(x[0], x[1]); w1 = pack_bf16x2(x[2], x[3]);
       w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
@@ -423,18 +427,21 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 // fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), biases come from the constant bank and are
 // added two at a time (add.f32x2).
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gsave, float& sigma) {
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gmask, float& sigma) {
   const int cbase = c.half * 128;
   uint32_t a0[16], a1[16];
   tmem_ld16(c.t_lane + cbase, a0);
 #pragma unroll 1
   for (int q = 0; q < 8; q += 2) {
+    uint32_t f0 = 0u, f1 = 0u;
     tmem_ld_wait();                                       // a0 (step q) has landed
     tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);       // step q+1 in flight
-    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, gsave, sigma);
+    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, f0, sigma);
     tmem_ld_wait();                                       // a1 has landed
     if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
-    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, gsave, sigma);
+    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, f1, sigma);
+    if (kSave && kRelu)  // 32 columns = one word of this thread's 16-byte mask row (a warp writes 32 rows x 4 B, 16 B apart)
+      *reinterpret_cast<uint32_t*>(gmask + ((size_t)(c.half * 128) + c.r) * 16 + (q >> 1) * 4) = fold_mask16(f0) | (fold_mask16(f1) << 16);
   }
 }
 
@@ -484,18 +491,18 @@ struct FwdEpi {
       else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, nullptr);
     }
     if (ml < 9) {
-      uint8_t* gsave = kSave ? p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536 : nullptr;
-      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
-      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);  // layers_2: no act.
-      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, gsave, st.sigma);
+      uint8_t* gmask = (kSave && ml < 8) ? p.saved + mask_tensor_off(ml, T) + (size_t)c.tile * 4096 : nullptr;
+      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);
+      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);  // layers_2: no act.
+      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);
     } else {
       // color_fc.0 epilogue (128 columns, ReLU; this thread's half = 64 of them) + color_fc.2
       // (128 -> 3) on CUDA cores; the two halves of a row meet through the (now free) E buffer
-      uint8_t* gsave = kSave ? p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768 : nullptr;
       float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
         const int col0 = c.half * 64 + q * 32;
+        uint32_t f0 = 0u, f1 = 0u;
         uint32_t a[32];
         tmem_ld32(c.t_lane + col0, a);
         tmem_ld_wait();
@@ -511,10 +518,18 @@ struct FwdEpi {
             rgb[1] = fmaf(x[e], w[128 + 8 * j + e], rgb[1]);
             rgb[2] = fmaf(x[e], w[256 + 8 * j + e], rgb[2]);
           }
-          if (kSave)  // c1 tile image -> A[slot] K-blocks 0,1 (free after color_fc.0's MMAs), bulk-stored by store_tile
-            st_shared_v4(c.a_img + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j)), pack_bf16x2(x[0], x[1]),
-                         pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+          if (kSave) {  // c1 tile image -> A[slot] K-blocks 0,1 (free after color_fc.0's MMAs), bulk-stored by store_tile
+            const uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
+                           w3 = pack_bf16x2(x[6], x[7]);
+            st_shared_v4(c.a_img + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j)), w0, w1, w2, w3);
+            uint32_t& f = (j < 2) ? f0 : f1;      // 16-column steps: j = 0,1 and j = 2,3
+            add_pair_flags(f, w0, 4 * (j & 1)); add_pair_flags(f, w1, 4 * (j & 1) + 1);
+            add_pair_flags(f, w2, 4 * (j & 1) + 2); add_pair_flags(f, w3, 4 * (j & 1) + 3);
+          }
         }
+        if (kSave)  // this thread's 64 columns of c1: 8-byte mask row, one word per 32 columns
+          *reinterpret_cast<uint32_t*>(p.saved + mask_tensor_off(8, T) + (size_t)c.tile * 2048 + ((size_t)(c.half * 128) + c.r) * 8 + q * 4) =
+              fold_mask16(f0) | (fold_mask16(f1) << 16);
       }
       const uint32_t xaddr = c.e_img + c.r * 16u;
       if (c.half == 1) st_shared_v4(xaddr, __float_as_uint(rgb[0]), __float_as_uint(rgb[1]), __float_as_uint(rgb[2]), __float_as_uint(st.sigma));
@@ -560,24 +575,18 @@ struct DgradEpi {
   static constexpr bool kBulkStore = true;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   static constexpr bool kReverseTiles = true;
-  struct State { float4 g; };
+  struct State { float4 g; uint4 mask; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
 
-  // The ReLU-mask source of layer l+1 (a 64 KB saved-activation tile written by the forward pass,
-  // long evicted) is pulled into L2 one layer ahead, so the epilogue's 16-byte loads are L2 hits.
-  __device__ static void prefetch(const Params& p, State&, const TileCtx& c, int l) {
-    if ((threadIdx.x & 255) != 0) return;
-    const int bl_next = l + 2;  // layer l+1 has bl = l+2 and masks with tensor 9 - bl
-    if (bl_next >= 2 && bl_next <= 9)
-#if NB_DG_L2HINT & 1
-      tma_prefetch_l2_hint(p.saved + saved_tensor_off(9 - bl_next, p.num_tiles) + (size_t)c.tile * 65536, 65536, l2_policy_evict_last());
-#else
-      tma_prefetch_l2(p.saved + saved_tensor_off(9 - bl_next, p.num_tiles) + (size_t)c.tile * 65536, 65536);
-#endif
-    if (l == 6) {  // c1 tile of this slot's NEXT 128-row tile (begin_tile masks delta_c1 with it)
-      const int64_t nt = c.tile + 4 * (int64_t)num_clusters_x();
-      if (nt < p.num_tiles) tma_prefetch_l2(p.saved + saved_tensor_off(9, p.num_tiles) + (size_t)nt * 32768, 32768);
-    }
+  // The ReLU mask of layer l is this thread's 16-byte row of the bit-mask tensor the forward pass wrote (one bit per
+  // element instead of the 64 KB bf16 activation tile): ONE load per thread and layer, issued before the accumulator
+  // wait, so its latency is off the epilogue's critical path (the per-thread loads of the activation tile used to
+  // account for 25 % of the kernel's stall samples, and for 1.1 GB of DRAM reads per step).
+  __device__ static void prefetch(const Params& p, State& st, const TileCtx& c, int l) {
+    const int bl = l + 1;       // masks with h_{9-bl}: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
+    if (bl >= 2)
+      st.mask = __ldg(reinterpret_cast<const uint4*>(p.saved + mask_tensor_off(9 - bl, p.num_tiles) + (size_t)c.tile * 4096 +
+                                                     ((size_t)(c.half * 128) + c.r) * 16));
   }
 
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
@@ -586,22 +595,24 @@ struct DgradEpi {
     st.g = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past M carry zero gradient
     if (m_raw < p.M) st.g = __ldg(reinterpret_cast<const float4*>(p.d_out) + m_raw);
     // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
-    const uint8_t* c1img = p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768;
-    uint8_t* dsave = p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768;
+    const uint2 cbits = __ldg(reinterpret_cast<const uint2*>(p.saved + mask_tensor_off(8, T) + (size_t)c.tile * 2048 +
+                                                             ((size_t)(c.half * 128) + c.r) * 8));
     const float* w = c.cf + kF32WC1;
     const uint32_t kb = (uint32_t)c.half;  // 128 columns: each half of the slot's threads takes 64
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t o = sw_off(c, kb, j);
-      const uint4 cm = __ldg(reinterpret_cast<const uint4*>(c1img + o));
+      // 8 columns = pairs 4*(j&1) .. +3 of the 16-column step j/2; steps 0,1 in cbits.x, 2,3 in cbits.y
+      const uint32_t field = ((j < 4 ? cbits.x : cbits.y) >> (16 * ((j >> 1) & 1))) & 0xFFFFu;
+      const int k0 = 4 * (j & 1);
       float x[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int col = c.half * 64 + j * 8 + e;
         x[e] = fmaf(st.g.z, w[256 + col], fmaf(st.g.y, w[128 + col], st.g.x * w[col]));
       }
-      const uint32_t w0 = mask_pos_bf16x2(pack_bf16x2(x[0], x[1]), cm.x), w1 = mask_pos_bf16x2(pack_bf16x2(x[2], x[3]), cm.y),
-                     w2 = mask_pos_bf16x2(pack_bf16x2(x[4], x[5]), cm.z), w3 = mask_pos_bf16x2(pack_bf16x2(x[6], x[7]), cm.w);
+      const uint32_t w0 = pack_bf16x2(x[0], x[1]) & pair_mask_word(field, k0), w1 = pack_bf16x2(x[2], x[3]) & pair_mask_word(field, k0 + 1),
+                     w2 = pack_bf16x2(x[4], x[5]) & pair_mask_word(field, k0 + 2), w3 = pack_bf16x2(x[6], x[7]) & pair_mask_word(field, k0 + 3);
       st_shared_v4(c.a_img + o, w0, w1, w2, w3);
     }
   }
@@ -622,17 +633,13 @@ struct DgradEpi {
   __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
     const int bl = l + 1;
     const int64_t T = p.num_tiles;
-    // ReLU mask source: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (layers_2 has no activation)
-    const uint8_t* himg = (bl >= 2) ? p.saved + saved_tensor_off(9 - bl, T) + (size_t)c.tile * 65536 : nullptr;
+    // ReLU mask (bit per element, loaded in prefetch): bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
+    const bool masked = bl >= 2;
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int col0 = c.half * 128 + q * 32;
       const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
-      uint4 hm[4];
-      if (himg) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hm[j] = __ldg(reinterpret_cast<const uint4*>(himg + sw_off(c, kb, j0 + j)));
-      }
+      const uint32_t mw = q == 0 ? st.mask.x : (q == 1 ? st.mask.y : (q == 2 ? st.mask.z : st.mask.w));   // two 16-column steps
       uint32_t a[32];
       tmem_ld32(c.t_lane + col0, a);
       tmem_ld_wait();
@@ -647,9 +654,11 @@ struct DgradEpi {
         }
         uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
                  w3 = pack_bf16x2(x[6], x[7]);
-        if (himg) {
-          w0 = mask_pos_bf16x2(w0, hm[j].x); w1 = mask_pos_bf16x2(w1, hm[j].y);
-          w2 = mask_pos_bf16x2(w2, hm[j].z); w3 = mask_pos_bf16x2(w3, hm[j].w);
+        if (masked) {
+          const uint32_t field = (mw >> (16 * (j >> 1))) & 0xFFFFu;
+          const int k0 = 4 * (j & 1);
+          w0 &= pair_mask_word(field, k0); w1 &= pair_mask_word(field, k0 + 1);
+          w2 &= pair_mask_word(field, k0 + 2); w3 &= pair_mask_word(field, k0 + 3);
         }
         st_shared_v4(c.a_img + sw_off(c, kb, j0 + j), w0, w1, w2, w3);
       }

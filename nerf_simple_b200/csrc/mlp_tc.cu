@@ -201,7 +201,17 @@ constexpr uint32_t kABytes = 65536, kEBytes = 16384;      // activation tile 128
 // (128 cols, 32 KB per tile), 10 = posx (64 cols, 16 KB), 11 = posd (32 of 64 cols, 16 KB).  Every
 // tile is stored as [K-block][128 rows x 128 B SWIZZLE_128B], i.e. exactly the UMMA operand image
 // the backward kernels bulk-copy back into shared memory (K-major for dgrad, MN-major for wgrad).
-constexpr size_t kSavedTileBytes = 9 * 65536 + 32768 + 16384 + 16384;
+constexpr size_t kSavedDataTileBytes = 9 * 65536 + 32768 + 16384 + 16384;
+// ReLU bit masks (training), written by the forward epilogue behind the saved tiles and read by the delta chain
+// instead of the 64 KB activation tiles themselves: one bit per element, 16 B per (row, column half) for h0..h7
+// (mask tensors 0..7, 4 KB per tile) and 8 B per (row, column half) for c1 (mask tensor 8, 2 KB per tile).
+// Within a 16-column step the bit of column 2k is bit k and the bit of column 2k+1 is bit 8+k of a 16-bit field
+// (what one HSET2 + LOP3 per bf16 pair produces and one SHIFT + PRMT per pair expands back into a word mask).
+constexpr size_t kMaskTileBytes = 8 * 4096 + 2048;
+constexpr size_t kSavedTileBytes = kSavedDataTileBytes + kMaskTileBytes;
+__host__ __device__ __forceinline__ size_t mask_tensor_off(int t, int64_t num_tiles) {
+  return (kSavedDataTileBytes + (size_t)t * 4096) * (size_t)num_tiles;
+}
 __host__ __device__ __forceinline__ size_t saved_tensor_off(int t, int64_t num_tiles) {
   const size_t per_tile = t < 9 ? (size_t)t * 65536 : (t == 9 ? 9 * 65536 : (t == 10 ? 9 * 65536 + 32768 : 9 * 65536 + 49152));
   return per_tile * (size_t)num_tiles;

@@ -265,6 +265,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return r;
 }
 
+// ReLU bit masks.  flags: 0xFFFF in each half of the result whose bf16 value is > 0 (one HSET2).
+__device__ __forceinline__ uint32_t pos_flags_bf16x2(uint32_t w) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  return __hgt2_mask(v, __float2bfloat162_rn(0.f));
+}
+// pack: pair k (0..7) of a 16-column step contributes bit k (even column) and bit 24+k (odd column) to `acc`;
+// fold_mask16 brings the odd-column flags down to bits 8..15.
+__device__ __forceinline__ void add_pair_flags(uint32_t& acc, uint32_t w, int k) {
+  acc |= pos_flags_bf16x2(w) & ((1u << k) | (1u << (24 + k)));
+}
+__device__ __forceinline__ uint32_t fold_mask16(uint32_t acc) { return (acc & 0xFFu) | (acc >> 16); }
+// unpack: 16-bit field -> 0xFFFF / 0x0000 per half for pair k (shift the two flags to the byte MSBs, PRMT replicates them)
+__device__ __forceinline__ uint32_t pair_mask_word(uint32_t field16, int k) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(r) : "r"(field16 << (7 - k)));
+  return r;
+}
+
 // One lane of a fully converged warp (the MMA warp runs its loops warp-uniformly so that the
 // descriptors live in uniform registers; only the tcgen05 instructions are elected).
 __device__ __forceinline__ bool elect_one() {
