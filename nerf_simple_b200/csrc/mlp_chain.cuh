@@ -13,6 +13,9 @@
 //                      it must finish inside the 2048 cycles the other slot's MMAs take)
 //   warp  16         : weight producer (TMA bulk copy of this CTA's half slab)
 //   warp  17         : leader CTA: MMA issuer.  peer CTA: forwards "my half slab landed" to the leader.
+//   warps 18, 19     : training kernels only: bulk-store issuer of slot 0 / 1.  The epilogue warps hand a finished
+//                      tile image over through an mbarrier (one arrive per warp) and get the buffer back through
+//                      another one, instead of two 256-thread bar.syncs and a serial leader thread per layer.
 //
 // The same skeleton runs the forward chain (FwdEpi) and the backward delta chain (DgradEpi); they
 // differ only in the slab schedule and in what the epilogue warps do with each accumulator.
@@ -21,10 +24,11 @@ constexpr int kCStages = 4;
 constexpr uint32_t kCStageBytes = 16384;
 constexpr uint32_t kC_Bar = kC_W + kCStages * kCStageBytes;  // 229376
 constexpr uint32_t kCSmemLaunch = kC_Bar + 256 + 1024;
-constexpr int kCThreads = 576;
-constexpr int kCProducerWarp = 16, kCMmaWarp = 17;
+constexpr int kCThreads = 640;
+constexpr int kCProducerWarp = 16, kCMmaWarp = 17, kCStoreWarp0 = 18;
 // barrier offsets inside the barrier block
-constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128;
+constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128, kB_Written = 136,
+                   kB_StoreFree = 152;
 
 __constant__ float c_f32[kConstSlots * kF32Floats];  // biases / head weights of the nets being run (slot per packed buffer, uploaded per call)
 
@@ -62,9 +66,10 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       mbar_init(bar + kB_WEmpty + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      // inference: one elected arrive per epilogue warp (8 warps x 2 CTAs); training: one per slot per CTA
-      mbar_init(bar + kB_Act + 8 * s, Epi::kBulkStore ? 2 : 16);
+      mbar_init(bar + kB_Act + 8 * s, 16);   // one elected arrive per epilogue warp (8 warps x 2 CTAs)
       mbar_init(bar + kB_Acc + 8 * s, 1);
+      mbar_init(bar + kB_Written + 8 * s, 8);    // this CTA's 8 epilogue warps of the slot: "tile image complete"
+      mbar_init(bar + kB_StoreFree + 8 * s, 1);  // the slot's store warp: "the bulk store has read the image"
     }
     fence_mbar_init();
   }
@@ -96,57 +101,47 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
     c.cf = c_f32 + p.cslot * kF32Floats;
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
-    uint32_t acc_parity = 0;
+    uint32_t acc_parity = 0, free_parity = 0;
     typename Epi::State st;
-    const bool slot_leader = (threadIdx.x & 255) == 0;  // issues this slot's bulk stores (training kernels)
+    bool first_step = true;
+    // hand a finished tile image to the MMA warp (leader's act barrier) and, in the training kernels, to this slot's
+    // store warp; `to_mma` is false after the last layer of a tile
+    auto publish = [&](bool to_mma) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (Epi::kBulkStore) mbar_arrive(bar + kB_Written + 8 * slot);
+        if (to_mma) mbar_arrive_cluster(act_remote);
+      }
+    };
+    // before overwriting A[slot] / E[slot]: the bulk store of the previous image must have read it
+    auto reclaim = [&]() {
+      if (Epi::kBulkStore && !first_step) {
+        mbar_wait(bar + kB_StoreFree + 8 * slot, free_parity, 500);
+        free_parity ^= 1;
+      }
+      first_step = false;
+    };
     for (int64_t k = slot; k < my_pt; k += 2) {
       c.tile = 2 * (cid + k * C) + rank;
       // the delta chain walks the tiles in REVERSE: the forward pass wrote the saved activations of the last
       // tiles last, so they are the ones still in L2 when the backward starts
       if (Epi::kReverseTiles) c.tile = 2 * (PT - 1 - (cid + k * C)) + rank;
-      if (Epi::kBulkStore) {  // the previous tile's last tile image must have left shared memory
-        if (slot_leader) tma_bulk_store_wait_read();
-        slot_barrier(slot);
-      }
+      reclaim();
       Epi::begin_tile(p, st, c);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      if (Epi::kBulkStore) {
-        slot_barrier(slot);
-        if (slot_leader) {
-          Epi::store_tile(p, c, -1);
-          mbar_arrive_cluster(act_remote);
-        }
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(act_remote);
-      }
+      publish(true);
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         Epi::prefetch(p, st, c, l);  // global loads that do not depend on the accumulator
         mbar_wait(bar + kB_Acc + 8 * slot, acc_parity, 100 + l);
         acc_parity ^= 1;
         tc_fence_after();
-        if (Epi::kBulkStore) {  // A[slot] is about to be overwritten: its bulk store must have read it
-          if (slot_leader) tma_bulk_store_wait_read();
-          slot_barrier(slot);
-        }
+        reclaim();
         Epi::layer(p, st, c, l);
-        tc_fence_before();
-        if (Epi::kBulkStore) {
-          fence_proxy_async_smem();
-          slot_barrier(slot);
-          if (slot_leader) {
-            Epi::store_tile(p, c, l);
-            if (l + 1 < Epi::kNumLayers) mbar_arrive_cluster(act_remote);
-          }
-        } else if (l + 1 < Epi::kNumLayers) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(act_remote);
-        }
+        if (Epi::kBulkStore || l + 1 < Epi::kNumLayers) publish(l + 1 < Epi::kNumLayers);
       }
     }
-    if (Epi::kBulkStore && slot_leader) tma_bulk_store_wait_read();
+    if (Epi::kBulkStore && !first_step) mbar_wait(bar + kB_StoreFree + 8 * slot, free_parity, 501);   // last store read its image
   } else if (warp == kCProducerWarp) {
     // ==================================== weight producer ====================================
     if (lane == 0) {
@@ -173,6 +168,28 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
           s0 = s1 + 1;
         }
       }
+    }
+  } else if (warp >= kCStoreWarp0) {
+    // ============================ bulk-store issuer of one slot (training) ============================
+    if (Epi::kBulkStore && lane == 0) {
+      const int slot = warp - kCStoreWarp0;
+      TileCtx c;
+      c.slot = slot;
+      c.a_img = smem_base + kC_A + slot * kABytes;
+      c.e_img = smem_base + kC_E + slot * kEBytes;
+      uint32_t parity = 0;
+      for (int64_t k = slot; k < my_pt; k += 2) {
+        c.tile = 2 * (cid + k * C) + rank;
+        if (Epi::kReverseTiles) c.tile = 2 * (PT - 1 - (cid + k * C)) + rank;
+        for (int l = -1; l < Epi::kNumLayers; ++l) {
+          mbar_wait(bar + kB_Written + 8 * slot, parity, 600 + l);
+          parity ^= 1;
+          Epi::store_tile(p, c, l);          // shared -> global through the TMA engine
+          tma_bulk_store_wait_read();
+          mbar_arrive(bar + kB_StoreFree + 8 * slot);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all writes complete before the CTA exits
     }
   } else if (rank != 0) {
     // peer CTA: nothing to issue (its MMAs are issued by the leader, its TMA signals the leader)
