@@ -211,6 +211,14 @@ int nb200_adam_step_state(float* param, const float* grad, float* exp_avg, float
  * arrival / completion epochs there; the epoch is the optimizer step count of `state`).  Every rank must enqueue the
  * call once per step.  n (floats) must be a multiple of 4; world <= 8 (one NVSwitch domain). */
 #define NB200_P2P_FLAG_WORDS 32
+/* Peer-shareable device buffers (CUDA IPC) for nb200_adam_allreduce_p2p -- the ONLY entry points that allocate or
+ * synchronise.  nb200_p2p_alloc: cudaMalloc + zero `bytes` on the current device and export a 64-byte handle (send it
+ * to the other ranks of the node by any host channel).  nb200_p2p_open: map a peer's buffer for kernels of the CURRENT
+ * device (peer access over NVLink is enabled lazily by the driver).  close / free undo them. */
+int nb200_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int nb200_p2p_open(const void* handle64, void** dev_ptr);
+int nb200_p2p_close(void* dev_ptr);
+int nb200_p2p_free(void* dev_ptr);
 int nb200_adam_allreduce_p2p(float* param, const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
                              float* exp_avg, float* exp_avg_sq, int64_t n, const void* state, float beta1, float beta2,
                              float eps, nb200_stream_t stream);

@@ -49,6 +49,10 @@ SYMBOLS = {
     "nb200_select_rays_state": (_i, [_p, _p, _i64, _u64, _p, _i64, _p, _p, _p, _p]),
     "nb200_stratified_ts_state": (_i, [_u64, _p, _i64, _i, _f, _f, _p, _p]),
     "nb200_adam_step_state": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _p]),
+    "nb200_p2p_alloc": (_i, [_sz, C.POINTER(C.c_void_p), _p]),
+    "nb200_p2p_open": (_i, [_p, C.POINTER(C.c_void_p)]),
+    "nb200_p2p_close": (_i, [_p]),
+    "nb200_p2p_free": (_i, [_p]),
     "nb200_adam_allreduce_p2p": (_i, [_p, _p, _p, _i, _i, _p, _p, _i64, _p, _f, _f, _f, _p]),
     "nb200_frame_to_u8": (_i, [_p, _i64, _i, _p, _p]),
     "nb200_sample_pdf_merge": (_i, [_p, _p, _p, _i, _u64, _u64, _i64, _i, _i, _p, _p]),

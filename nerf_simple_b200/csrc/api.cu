@@ -57,4 +57,39 @@ const char* nb200_error_string(int code) {
 
 const char* nb200_last_cuda_error(void) { return nb200::g_last_cuda_error; }
 
+// ---- peer-shareable device buffers (CUDA IPC): the only entry points that allocate.  A buffer is cudaMalloc'ed by
+// its owner, exported as a 64-byte handle, and opened by the other ranks of the node WITH THEIR OWN DEVICE CURRENT, which
+// is what maps it for that device's kernels over NVLink (cudaIpcMemLazyEnablePeerAccess).
+int nb200_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return NB200_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  NB_CUDA_CHECK(cudaMalloc(&p, bytes));
+  NB_CUDA_CHECK(cudaMemset(p, 0, bytes));
+  NB_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return nb200::record_cuda_error(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return NB200_OK;
+}
+int nb200_p2p_open(const void* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return NB200_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  NB_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NB200_OK;
+}
+int nb200_p2p_close(void* dev_ptr) {
+  if (!dev_ptr) return NB200_ERR_ARG;
+  NB_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+  return NB200_OK;
+}
+int nb200_p2p_free(void* dev_ptr) {
+  if (!dev_ptr) return NB200_ERR_ARG;
+  NB_CUDA_CHECK(cudaFree(dev_ptr));
+  return NB200_OK;
+}
+
 }  // extern "C"

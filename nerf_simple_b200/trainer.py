@@ -35,36 +35,79 @@ def flatten_parameters(net):
     return flat
 
 
-def attach_flat_grad(net, device=None):
+def attach_flat_grad(net, device=None, flat=None):
     params = list(net.parameters())
     shapes = [tuple(p.shape) for p in params]
-    flat = torch.zeros(flat_size(shapes), dtype=torch.float32, device=device or params[0].device)
+    if flat is None:
+        flat = torch.zeros(flat_size(shapes), dtype=torch.float32, device=device or params[0].device)
     for p, v in zip(params, flat_views(flat, shapes)):
         p.grad = v
     return flat
 
 
-def share_peer_buffers(local, group=None):
-    """Map the CUDA tensor `local` of every rank of `group` into this process (CUDA IPC through torch's own storage
-    sharing, the mechanism torch.multiprocessing uses) and return the list of `world` tensors, index = rank, own
-    tensor included.  Peer access between the devices is switched on by a first cross-device copy.  Raises when the
-    ranks are not on one node / have no peer access -- callers fall back to NCCL."""
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    descs = [None] * world
-    dist.all_gather_object(descs, reduce_tensor(local), group=group)      # (rebuild function, IPC handle + layout)
-    out = []
-    for r, (rebuild, args) in enumerate(descs):
-        if r == rank:
-            out.append(local)
-            continue
-        t = rebuild(*args)                     # cudaIpcOpenMemHandle: the peer's allocation in this address space
-        if t.device.index != local.device.index and not torch.cuda.can_device_access_peer(local.device.index, t.device.index):
-            raise RuntimeError(f"no peer access between cuda:{local.device.index} and cuda:{t.device.index}")
-        t.view(-1)[:1].to(local.device)       # first cross-device copy: torch enables peer access for the pair
-        out.append(t)
-    return out
+class PeerBuffer:
+    """A device buffer every rank of the node can address from its own kernels (NVLink / NVSwitch peer memory).
+    The owner allocates it through the C ABI (cudaMalloc + CUDA IPC export: torch's caching allocator hands out
+    interior pointers of segments it may recycle, and torch's own IPC import maps a peer buffer under the PEER's
+    device, which does not make it visible to kernels of this rank's device), the handles travel through
+    torch.distributed, and every rank opens the others' with its own device current."""
+
+    def __init__(self, nbytes, device, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.device, self.nbytes, self.group = device, int(nbytes), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.nb200_p2p_alloc(self.nbytes, C.byref(ptr), handle), "nb200_p2p_alloc")
+        self.ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (handle.raw, self.nbytes), group=group)
+        self.ptrs, self._opened = [], []
+        for r, (h, nb) in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.ptr)
+                continue
+            if nb != self.nbytes:
+                raise RuntimeError("ranks disagree on the peer buffer size")
+            q = C.c_void_p()
+            with torch.cuda.device(device):      # opened under THIS rank's device: its kernels will dereference it
+                _lib.check(lib.nb200_p2p_open(h, C.byref(q)), f"nb200_p2p_open (rank {r})")
+            self.ptrs.append(q.value)
+            self._opened.append(q.value)
+
+    def tensor(self, dtype, numel, byte_offset=0):
+        """This rank's own buffer as a torch tensor (shares the memory; keeps the buffer alive)."""
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        owner = self
+
+        class _Iface:
+            __cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (self.ptr + byte_offset, False),
+                                        "version": 2, "strides": None}
+            keep = owner
+        assert byte_offset + numel * itemsize <= self.nbytes
+        return torch.as_tensor(_Iface(), device=self.device)
+
+    def ptr_array(self, byte_offset=0):
+        import ctypes as C
+        return (C.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
+
+    def release(self):
+        lib = _lib.load()
+        for q in self._opened:
+            lib.nb200_p2p_close(C_void(q))
+        self._opened = []
+        if self.ptr:
+            lib.nb200_p2p_free(C_void(self.ptr))
+            self.ptr = None
+
+
+def C_void(v):
+    import ctypes as C
+    return C.c_void_p(v)
 
 
 def allreduce_mean_(flat_grad, world_size, group=None):
@@ -109,7 +152,16 @@ class Trainer:
         if self.world_size > 1:
             import torch.distributed as dist
             dist.broadcast(self.flat_param, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        self.flat_grad = attach_flat_grad(net)
+        # Multi-rank steps: the gradient all-reduce is fused into the Adam kernel over NVLink peer memory
+        # (nb200_adam_allreduce_p2p), so a step stays ONE graph replay; the flat gradient then lives in a peer-shareable
+        # buffer.  NB200_P2P_ALLREDUCE=0, or ranks without peer access, use NCCL instead: two graphs are replayed around
+        # the eagerly launched collective (capturing the NCCL all-reduce itself inside torch.cuda.graph hung on this
+        # stack -- torch 2.11, NCCL 2.28.9 -- in every capture mode).
+        self._p2p, self.p2p_error = None, None
+        flat_grad = None
+        if self.world_size > 1 and os.environ.get("NB200_P2P_ALLREDUCE", "1") == "1" and self.flat_param.is_cuda:
+            flat_grad = self._setup_p2p()
+        self.flat_grad = attach_flat_grad(net, flat=flat_grad)
         self.params = net.kernel_params()
         self.grads = [p.grad for p in self.params]
         # train.py:43 Adam(lr=5e-4, betas=(0.9,0.999), eps=1e-8) with a per-step exponential lr decay
@@ -143,38 +195,35 @@ class Trainer:
         self._grad_ptrs = _lib.ptr_array(self.grads)
         self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
                             if self.precision == _lib.BF16 else None)
-        # Multi-rank steps: the gradient all-reduce is fused into the Adam kernel over NVLink peer memory
-        # (nb200_adam_allreduce_p2p), so a step stays ONE graph replay.  NB200_P2P_ALLREDUCE=0, or ranks without peer
-        # access, use NCCL instead: two graphs are replayed around the eagerly launched collective (capturing the NCCL
-        # all-reduce itself inside torch.cuda.graph hung on this stack -- torch 2.11, NCCL 2.28.9 -- in every capture mode).
         self.use_graph = bool(use_graph) and self.precision == _lib.BF16 and self.N % 4 == 0 and self.N <= 1024
-        self._p2p, self.p2p_error = None, None
-        if self.world_size > 1 and os.environ.get("NB200_P2P_ALLREDUCE", "1") == "1" and self.flat_grad.is_cuda:
-            self._setup_p2p()
         self._graphs, self.graph_error = {}, None
         self.launches = 0
         self.part_events = []
         self.last_loss = None
 
     def _setup_p2p(self):
-        """Exchange the flat gradient buffers and the flag blocks with the other ranks (same node, <= 8 ranks)."""
+        """Allocate the flat gradient + the flag block in a peer-shareable buffer and map the other ranks' (same node,
+        <= 8 ranks).  Returns the gradient tensor, or None when any rank failed (all ranks then use NCCL)."""
         import torch.distributed as dist
         ok = torch.ones(1, device=self.device)
+        flat = None
         try:
             if self.world_size > 8:
                 raise RuntimeError("more than 8 ranks")
-            self._p2p_flags = torch.zeros(_lib.P2P_FLAG_WORDS, dtype=torch.int32, device=self.device)
-            grads = share_peer_buffers(self.flat_grad, self.group)
-            flags = share_peer_buffers(self._p2p_flags, self.group)
-            self._p2p = (grads, flags, _lib.ptr_array(grads), _lib.ptr_array(flags))
+            n = self.flat_param.numel()
+            flag_off = (n * 4 + 255) // 256 * 256
+            buf = PeerBuffer(flag_off + _lib.P2P_FLAG_WORDS * 4, self.device, self.group)
+            flat = buf.tensor(torch.float32, n)
+            self._p2p = (buf, buf.ptr_array(0), buf.ptr_array(flag_off))
         except Exception as e:      # noqa: BLE001 -- any failure means "use NCCL"; recorded, and agreed on by all ranks below
             self.p2p_error = repr(e)
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank takes the same path
         if float(ok) == 0.0:
-            self._p2p = None
+            self._p2p, flat = None, None
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
+        return flat
 
     # ------------------------------------------------------------------------------------------ one step
     def _enqueue_step(self, time_parts=False, part="all", select=True, sample=True):
@@ -242,7 +291,7 @@ class Trainer:
     def _enqueue_update(self, lib, state, st):
         B, M = self.B, self.B * self.N
         if self._p2p is not None:   # all-reduce fused into Adam: peers' gradients are read over NVLink inside the kernel
-            _lib.check(lib.nb200_adam_allreduce_p2p(_lib.ptr(self.flat_param), self._p2p[2], self._p2p[3], self.rank, self.world_size,
+            _lib.check(lib.nb200_adam_allreduce_p2p(_lib.ptr(self.flat_param), self._p2p[1], self._p2p[2], self.rank, self.world_size,
                                                     _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), state,
                                                     self.betas[0], self.betas[1], self.eps, st), "nb200_adam_allreduce_p2p")
         else:

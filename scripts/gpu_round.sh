@@ -12,6 +12,9 @@ for st in $stages; do
     ref)    timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_ref.json 2> $out/${tag}_ref.err; echo "ref rc=$?"; tail -c 1500 $out/${tag}_ref.json ;;
     train)  timeout 600 python bench.py --workload train > $out/${tag}_train.json 2> $out/${tag}_train.err; echo "train rc=$?"; tail -c 2500 $out/${tag}_train.json; tail -3 $out/${tag}_train.err ;;
     traintests) timeout 900 python -m pytest tests/test_gpu_full_size.py tests/test_gpu_parity.py tests/test_gpu_training_loop.py -x -q -m gpu -k 'train or grad or trainer' > $out/${tag}_traintests.log 2>&1; echo "traintests rc=$?"; tail -4 $out/${tag}_traintests.log ;;
+    sanitize)
+      for tool in memcheck racecheck; do timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_stream_kernels.py > $out/${tag}_sanitizer_${tool}_stream.log 2>&1; tail -2 $out/${tag}_sanitizer_${tool}_stream.log; done
+      timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_chain_kernels.py > $out/${tag}_sanitizer_memcheck_chain.log 2>&1; tail -3 $out/${tag}_sanitizer_memcheck_chain.log ;;
     smoke)  timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $out/${tag}_smoke.log ;;
     ncu_launch)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_train.csv python bench.py --workload train --steps 3 --warmup 3 > $out/${tag}_ncu_train.log 2>&1
