@@ -292,7 +292,7 @@ def setup(args, local_rank, world):
     return c
 
 
-def bench_render(args, c, H, W, N, steps, warmup, fine=0, fused=False, e2e=True, api=True):
+def bench_render(args, c, H, W, N, steps, warmup, fine=0, fused=False, e2e=True, api=True, precision=None):
     """Frames-per-GPU render (weak scaling): value, MLP-kernel time, e2e through host buffers."""
     import torch
     import torch.distributed as dist
@@ -306,7 +306,7 @@ def bench_render(args, c, H, W, N, steps, warmup, fine=0, fused=False, e2e=True,
     poses = torch.stack(poses_to_render(4, -30, 30)).to(dev)
     n_poses = poses.shape[0]
     net_fine = Nerf().to(dev) if fine > 0 else None     # --fine 128: hierarchical extension (configs[3])
-    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=args.precision, net_fine=net_fine, Nf=fine, fused=fused)
+    rend = FrameRenderer(net, H, W, f, N=N, seed=1, precision=precision or args.precision, net_fine=net_fine, Nf=fine, fused=fused)
     n_rays = H * W
     # the frames of the dome path are gathered on rank 0 (16 B/ray), asynchronously: the collective of frame i runs under
     # the kernels of frame i+1 (two send buffers); no rank ever receives frames it does not need
@@ -603,6 +603,12 @@ def b200_arm(args, rank, local_rank, world):
         line["n128"] = {"value": r128["value"], "unit": "rays/s", "ms_per_step": r128["ms_per_step"], "samples_per_sec": r128["value"] * 128,
                         "mlp_tflops": FLOP_FWD * H * W * 128 / (r128["mlp_ms"] * 1e-3) / 1e12,
                         "config": f"same frames at the reference's default N=128 (configs/lego.yaml:6, utils/rendering.py:102,145)"}
+        if world == 1:
+            rx3 = bench_render(args, c, H, W, N, max(3, args.steps // 4), 2, e2e=False, api=False, precision="bf16x3")
+            line["parity_mode_bf16x3"] = {"value": rx3["value"], "unit": "rays/s", "ms_per_step": rx3["ms_per_step"],
+                                          "mlp_tflops_algorithmic": FLOP_FWD * M / (rx3["mlp_ms"] * 1e-3) / 1e12, "dtype": "bf16x3",
+                                          "config": "same frames in the tensor-core fp32-class mode (error-compensated bf16, 3 MMA passes per K-block; "
+                                                    "max abs err <= 1e-4 vs the reference, tests/test_gpu_parity.py); the SIMT fp32 mode runs at ~25 TFLOP/s"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(args)

@@ -43,7 +43,11 @@ enum {
 /* precision of the MLP path */
 enum {
   NB200_FP32 = 0, /* fp32 SIMT layer kernels; parity mode, max-abs err <= 1e-4 vs reference    */
-  NB200_BF16 = 1  /* fused tcgen05 kernel, bf16 operands + fp32 accumulate in TMEM; <= 1e-2    */
+  NB200_BF16 = 1, /* fused tcgen05 kernel, bf16 operands + fp32 accumulate in TMEM; <= 1e-2    */
+  NB200_BF16X3 = 2 /* the same tcgen05 chain with error-compensated bf16 (hi/lo images of activations and
+                      weights, three MMA passes per K-block): fp32-class accuracy (<= 1e-4, also with weights
+                      scaled x1.5) on the tensor cores.  Forward / inference only: nb200_mlp_forward with
+                      saved == NULL; its packed buffer has its own size and layout. */
 };
 
 /* input mode of the MLP kernels */

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NERF_B200_LIB", os.path.join(_HERE, "libnerf_b200.so"))   # override: A/B builds
 
 OK = 0
-FP32, BF16 = 0, 1
+FP32, BF16, BF16X3 = 0, 1, 2
 IN_POINTS, IN_RAYS = 0, 1
 TRAIN_STATE_BYTES = 32     # NB200_TRAIN_STATE_BYTES
 P2P_FLAG_WORDS = 32        # NB200_P2P_FLAG_WORDS

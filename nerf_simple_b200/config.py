@@ -4,7 +4,9 @@ from __future__ import annotations
 import os
 
 _state = {
-    # "bf16": fused tcgen05 kernel (throughput mode, <=1e-2 parity); "fp32": SIMT parity mode (<=1e-4)
+    # "bf16": fused tcgen05 kernel (throughput mode, <=1e-2 parity); "fp32": SIMT parity mode (<=1e-4);
+    # "bf16x3": error-compensated bf16 on the tensor cores (<=1e-4 parity at a few hundred TFLOP/s; forward only --
+    # calls that need gradients run the fp32 kernels)
     "precision": os.environ.get("NERF_B200_PRECISION", "bf16"),
     # "reference": draw torch.rand(B,N) from the CPU global generator exactly like
     # utils/rendering.py:28 (bit-identical ts);  "philox": counter-based generator on the device.
@@ -25,8 +27,8 @@ _state = {
 
 
 def set_precision(p: str):
-    if p not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if p not in ("bf16", "fp32", "bf16x3"):
+        raise ValueError("precision must be 'bf16', 'fp32' or 'bf16x3'")
     _state["precision"] = p
 
 

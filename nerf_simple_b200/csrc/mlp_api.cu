@@ -11,10 +11,11 @@ int fp32_forward(int in_mode, const float* in0, const float* in1, int64_t M, int
 int fp32_backward(int64_t M, const float* const* P, const float* d_out, const void* saved,
                   float* const* G, void* scratch, size_t scratch_bytes, cudaStream_t s);
 // mlp_tc.cu
-size_t tc_packed_bytes();
+size_t tc_packed_bytes(int x3);
 size_t tc_saved_bytes(int64_t M);
 size_t tc_scratch_bytes(int64_t M, int train);
-int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s);
+int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s);
+int tc_forward_x3(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed, float* out, cudaStream_t s);
 int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
                float* out, void* saved, void* scratch, size_t scratch_bytes, cudaStream_t s);
 int tc_backward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
@@ -28,30 +29,30 @@ int tc_render(const float* rays, const float* poses, int H, int W, float f, int6
 extern "C" {
 
 size_t nb200_packed_weights_bytes(int precision) {
-  return precision == NB200_BF16 ? nb200::tc_packed_bytes() : 0;
+  return precision == NB200_BF16 ? nb200::tc_packed_bytes(0) : (precision == NB200_BF16X3 ? nb200::tc_packed_bytes(1) : 0);
 }
 
 int nb200_pack_weights(int precision, const float* const* params, void* packed, nb200_stream_t stream) {
   if (precision == NB200_FP32) return NB200_OK;
-  if (precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;
+  if (precision != NB200_BF16 && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
   if (!params || !packed) return NB200_ERR_ARG;
   for (int i = 0; i < 24; ++i)
     if (!params[i]) return NB200_ERR_ARG;
-  return nb200::tc_pack_weights(params, packed, nb200::as_stream(stream));
+  return nb200::tc_pack_weights(params, packed, precision == NB200_BF16X3, nb200::as_stream(stream));
 }
 
 size_t nb200_mlp_saved_bytes(int precision, int64_t M) {
-  if (M < 0) return 0;
+  if (M < 0 || precision == NB200_BF16X3) return 0;   // bf16x3 is an inference mode
   return precision == NB200_BF16 ? nb200::tc_saved_bytes(M) : nb200::fp32_saved_bytes(M);
 }
 
 size_t nb200_mlp_scratch_bytes(int precision, int64_t M, int train) {
-  if (M < 0) return 0;
+  if (M < 0 || precision == NB200_BF16X3) return 0;
   return precision == NB200_BF16 ? nb200::tc_scratch_bytes(M, train) : nb200::fp32_scratch_bytes(M, train);
 }
 
 static int check_common(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N) {
-  if (precision != NB200_FP32 && precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;
+  if (precision != NB200_FP32 && precision != NB200_BF16 && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
   if (in_mode != NB200_IN_POINTS && in_mode != NB200_IN_RAYS) return NB200_ERR_ARG;
   if (M < 0) return NB200_ERR_ARG;
   if (in_mode == NB200_IN_RAYS && (N < 1 || M % N != 0)) return NB200_ERR_ARG;
@@ -72,6 +73,10 @@ int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float*
                                nb200::as_stream(stream));
   }
   if (!packed) return NB200_ERR_ARG;
+  if (precision == NB200_BF16X3) {
+    if (saved) return NB200_ERR_UNSUPPORTED;   // forward / inference only: train in NB200_FP32 or NB200_BF16
+    return nb200::tc_forward_x3(in_mode, in0, in1, M, N, packed, out, nb200::as_stream(stream));
+  }
   return nb200::tc_forward(in_mode, in0, in1, M, N, packed, out, saved, scratch, scratch_bytes,
                            nb200::as_stream(stream));
 }
@@ -85,6 +90,7 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
   if (!grads) return NB200_ERR_ARG;
   for (int i = 0; i < 24; ++i)
     if (!grads[i]) return NB200_ERR_ARG;
+  if (precision == NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
   if (M == 0) return NB200_OK;  // gradients are accumulated into: nothing to add
   if (!d_out || !saved || ((uintptr_t)d_out & 15) || ((uintptr_t)in0 & 7)) return NB200_ERR_ARG;
   if (precision == NB200_FP32) {

@@ -36,6 +36,7 @@ struct TileCtx {
   int64_t tile;      // 128-row tile index
   int slot;          // which in-flight tile of the CTA
   int half;          // 0: accumulator columns [0,128), 1: [128,256)
+  int part;          // single-slot kernels (16 warps on one tile): accumulator columns [64 part, 64 part + 64)
   uint32_t r;        // row in tile == TMEM lane
   uint32_t rowoff;   // r * 128
   uint32_t r7s;      // (r & 7) << 4
@@ -66,7 +67,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       mbar_init(bar + kB_WEmpty + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar + kB_Act + 8 * s, 16);   // one elected arrive per epilogue warp (8 warps x 2 CTAs)
+      mbar_init(bar + kB_Act + 8 * s, 16 * (3 - Epi::kSlots));   // one elected arrive per epilogue warp (8 or 16 warps x 2 CTAs)
       mbar_init(bar + kB_Acc + 8 * s, 1);
       mbar_init(bar + kB_Written + 8 * s, 8);    // this CTA's 8 epilogue warps of the slot: "tile image complete"
       mbar_init(bar + kB_StoreFree + 8 * s, 1);  // the slot's store warp: "the bulk store has read the image"
@@ -89,10 +90,11 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
 
   if (warp < 16) {
     // ============================ prologue + epilogue of one slot ============================
-    const int slot = warp >> 3;
+    const int slot = Epi::kSlots == 2 ? warp >> 3 : 0;
     TileCtx c;
     c.slot = slot;
     c.half = (warp >> 2) & 1;
+    c.part = warp >> 2;
     c.r = (uint32_t)(warp & 3) * 32u + (uint32_t)lane;
     c.rowoff = c.r * 128u;
     c.r7s = (c.r & 7u) << 4;
@@ -123,7 +125,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       }
       first_step = false;
     };
-    for (int64_t k = slot; k < my_pt; k += 2) {
+    for (int64_t k = slot; k < my_pt; k += Epi::kSlots) {
       c.tile = 2 * (cid + k * C) + rank;
       // the delta chain walks the tiles in REVERSE: the forward pass wrote the saved activations of the last
       // tiles last, so they are the ones still in L2 when the backward starts
@@ -146,8 +148,8 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // ==================================== weight producer ====================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
-        const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
+      for (int64_t pr = 0; pr * Epi::kSlots < my_pt; ++pr) {
+        const int nslots = (Epi::kSlots == 2 && my_pt - 2 * pr >= 2) ? 2 : 1;
         int s0 = 0;
         for (int l = 0; l < Epi::kNumLayers; ++l) {
           int s1 = s0;
@@ -201,8 +203,8 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     uint32_t act_parity0 = 0, act_parity1 = 0;
     long long t_act = 0, t_wfull = 0, t_wpeer = 0, t_begin = clock64();
     const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);  // LBO/SBO/version/swizzle bits
-    for (int64_t pr = 0; pr * 2 < my_pt; ++pr) {
-      const int nslots = (my_pt - 2 * pr >= 2) ? 2 : 1;
+    for (int64_t pr = 0; pr * Epi::kSlots < my_pt; ++pr) {
+      const int nslots = (Epi::kSlots == 2 && my_pt - 2 * pr >= 2) ? 2 : 1;
       int s0 = 0;
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         int s1 = s0;
@@ -239,6 +241,15 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
               if (ksteps > 2) {
                 umma_bf16_2cta(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
                 umma_bf16_2cta(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              }
+              if (Epi::kSplit3 && slabs[s].amode) {   // bf16x3: the same B slab against the residual image A_lo (the other slot's buffer)
+                const uint64_t alo = adesc + ((slabs[s].src ? kEBytes : kABytes) >> 4);
+                umma_bf16_2cta(d_tmem, alo, bdesc, idesc, 1u);
+                umma_bf16_2cta(d_tmem, alo + 2, bdesc + 2, idesc, 1u);
+                if (ksteps > 2) {
+                  umma_bf16_2cta(d_tmem, alo + 4, bdesc + 4, idesc, 1u);
+                  umma_bf16_2cta(d_tmem, alo + 6, bdesc + 6, idesc, 1u);
+                }
               }
               if (release) umma_commit_2cta(bar + kB_WEmpty + 8 * stage);
               if (s == s1) umma_commit_2cta(bar + kB_Acc + 8 * slot);
@@ -468,6 +479,8 @@ struct FwdEpi {
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
+  static constexpr int kSlots = 2;
+  static constexpr bool kSplit3 = false;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
   struct State {
@@ -581,6 +594,153 @@ struct FwdEpi {
   }
 };
 
+// ============================================================ forward, NB200_BF16X3 (fp32-class accuracy)
+// Error-compensated bf16: every activation is kept as a pair of bf16 images, hi = bf16(x) and lo = bf16(x - hi), and
+// every weight as (W_hi, W_lo); a K-block costs three MMA passes, A_hi W_hi + A_lo W_hi + A_hi W_lo (the lo x lo term
+// is below 2^-16 relative and dropped), all accumulated in fp32 in TMEM.  The lo images live in the buffers the bf16
+// kernels use for their second in-flight tile, so ONE tile per CTA is in flight and all 16 epilogue warps work on it
+// (four per TMEM lane group, 64 accumulator columns each).  Replaces the 25 TFLOP/s SIMT kernels as the <= 1e-4
+// parity mode of utils/nets.py:34-43 for inference.
+__device__ __forceinline__ void split_hi_lo(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  lo = pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
+}
+template <int L, int J0, int J1>
+__device__ __forceinline__ void encode_row3(const float* x, uint32_t img_hi, uint32_t img_lo, uint32_t r) {
+  float f[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) f[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    f[c] = x[c];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {   // fp32-class mode: every level with the accurate sincosf (no double-angle recurrence)
+      float sv, cv;
+      sincosf(ldexpf(x[c], i), &sv, &cv);   // (2^i) * x is exact, as in utils/xyz.py:12
+      f[3 + c * 2 * L + 2 * i] = sv;
+      f[3 + c * 2 * L + 2 * i + 1] = cv;
+    }
+  }
+#pragma unroll
+  for (int j = J0; j < J1; ++j) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_hi_lo(f[8 * j + 2 * e], f[8 * j + 2 * e + 1], h[e], l[e]);
+    st_shared_v4(img_hi + sw128_off(r, j), h[0], h[1], h[2], h[3]);
+    st_shared_v4(img_lo + sw128_off(r, j), l[0], l[1], l[2], l[3]);
+  }
+}
+
+struct FwdEpi3 {
+  using Params = FwdEpiParams;
+  static constexpr bool kHasDbg = false;
+  static constexpr bool kBulkStore = false;
+  static constexpr int kSlots = 1;
+  static constexpr bool kSplit3 = true;
+  static constexpr int kNumLayers = kNumMmaLayers;
+  static constexpr bool kReverseTiles = false;
+  struct State {
+    float v[6];
+    float sigma;      // this thread's share (64 columns) of the sigma head
+    int64_t m_raw;
+    bool row_valid;
+  };
+  __device__ static const SlabDesc* slabs() { return c_layout.fwd3; }
+  __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
+  __device__ static void store_tile(const Params&, const TileCtx&, int) {}
+
+  __device__ static void encode(const float* x, const TileCtx& c, bool dirs) {
+    const uint32_t hi = c.e_img, lo = c.e_img + kEBytes;
+    if (!dirs) {
+      if (c.part == 0) encode_row3<kLp, 0, 2>(x, hi, lo, c.r);
+      else if (c.part == 1) encode_row3<kLp, 2, 4>(x, hi, lo, c.r);
+      else if (c.part == 2) encode_row3<kLp, 4, 6>(x, hi, lo, c.r);
+      else encode_row3<kLp, 6, 8>(x, hi, lo, c.r);
+    } else {
+      if (c.part == 0) encode_row3<kLd, 0, 2>(x, hi, lo, c.r);
+      else if (c.part == 1) encode_row3<kLd, 2, 4>(x, hi, lo, c.r);
+      else if (c.part == 2) encode_row3<kLd, 4, 6>(x, hi, lo, c.r);
+      else encode_row3<kLd, 6, 8>(x, hi, lo, c.r);
+    }
+  }
+
+  __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
+    st.m_raw = c.tile * kTileM + c.r;
+    st.row_valid = st.m_raw < p.M;
+    float t;
+    load_query_chain<false>(p, st.row_valid ? st.m_raw : p.M - 1, st.v, t);
+    st.sigma = 0.f;
+    encode(st.v, c, false);
+  }
+
+  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int ml) {
+    if (ml == 5) encode(st.v + 3, c, true);   // posx consumed by the skip layer: the encoding buffers now carry posd
+    const uint32_t a_hi = c.a_img, a_lo = c.a_img + kABytes;
+    if (ml < 9) {
+      const int cbase = c.part * 64;
+      const float* b = c.cf + kF32Bias + ml * 256;
+      const float* ws = c.cf + kF32WSig;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int col0 = cbase + q * 16;
+        uint32_t a[16];
+        tmem_ld16(c.t_lane + col0, a);
+        tmem_ld_wait();
+        const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = __uint_as_float(a[8 * j + e]) + b[col0 + 8 * j + e];
+            if (ml != 8) x[e] = fmaxf(x[e], 0.f);                        // layers_2 has no activation (utils/nets.py:41)
+            if (ml == 7) st.sigma = fmaf(x[e], ws[col0 + 8 * j + e], st.sigma);   // sigma head reads h7 in fp32 (:40)
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_hi_lo(x[2 * e], x[2 * e + 1], h[e], l[e]);
+          const uint32_t o = sw_off(c, kb, j0 + j);
+          st_shared_v4(a_hi + o, h[0], h[1], h[2], h[3]);
+          st_shared_v4(a_lo + o, l[0], l[1], l[2], l[3]);
+        }
+      }
+    } else {
+      // color_fc.0 epilogue (128 columns, 32 per thread, ReLU) + color_fc.2 (128 -> 3) in fp32 on CUDA cores; the four
+      // threads of a row meet through the (now free) encoding buffer
+      const int col0 = c.part * 32;
+      uint32_t a[32];
+      tmem_ld32(c.t_lane + col0, a);
+      tmem_ld_wait();
+      const float* b = c.cf + kF32Bias + 9 * 256 + col0;
+      const float* w = c.cf + kF32WC1 + col0;
+      float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float x = fmaxf(__uint_as_float(a[e]) + b[e], 0.f);
+        rgb[0] = fmaf(x, w[e], rgb[0]);
+        rgb[1] = fmaf(x, w[128 + e], rgb[1]);
+        rgb[2] = fmaf(x, w[256 + e], rgb[2]);
+      }
+      const uint32_t xaddr = c.e_img + ((uint32_t)c.part * 128u + c.r) * 16u;
+      if (c.part != 0) st_shared_v4(xaddr, __float_as_uint(rgb[0]), __float_as_uint(rgb[1]), __float_as_uint(rgb[2]), __float_as_uint(st.sigma));
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (c.part == 0) {
+        float4 acc = make_float4(rgb[0], rgb[1], rgb[2], st.sigma);
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(c.e_img + ((uint32_t)q * 128u + c.r) * 16u));
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        if (st.row_valid)
+          reinterpret_cast<float4*>(p.out)[st.m_raw] = make_float4(acc.x + c.cf[kF32BC1], acc.y + c.cf[kF32BC1 + 1], acc.z + c.cf[kF32BC1 + 2],
+                                                                   acc.w + c.cf[kF32BSig]);   // (r,g,b,sigma), utils/nets.py:43
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // the encoding buffers may be rewritten for the next tile
+    }
+  }
+};
+
 // ======================================================================= backward (dgrad)
 #ifndef NB_DG_L2HINT
 #define NB_DG_L2HINT 2   // bit 1: delta stores evict_first (511 -> 501 us).  bit 0 (mask prefetch evict_last, -6 us more) is off:
@@ -590,6 +750,8 @@ struct DgradEpi {
   using Params = BwdParams;
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = true;
+  static constexpr int kSlots = 2;
+  static constexpr bool kSplit3 = false;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   static constexpr bool kReverseTiles = true;
   struct State { float4 g; uint4 mask; };

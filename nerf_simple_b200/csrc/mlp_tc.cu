@@ -39,6 +39,9 @@ struct SlabDesc {
   uint8_t first;    // first slab of its layer (accumulator is overwritten)
   uint8_t last;     // last slab of its layer (commit to acc_full)
   uint8_t transposed;  // image(n,k) = W[(wcol0+k)*ldw + n] (dgrad operand) instead of W[n*ldw + wcol0+k]
+  uint8_t lo;          // bf16x3 mode: image of the residual W - bf16(W) instead of bf16(W)
+  uint8_t amode;       // bf16x3 mode: 1 = this slab multiplies A_hi and then A_lo, 0 = A_hi only
+  uint8_t pad[2];
 };
 
 struct PackedLayout {
@@ -48,6 +51,12 @@ struct PackedLayout {
   SlabDesc bwd[kMaxSlabs];  // dgrad chain: transposed weight images, 9 MMA layers
   uint32_t f32_off;  // fp32 section: bias[10][256] | wsig[256] | bsig(+pad 4) | wc1[3][128] | bc1[3](+pad)
   uint32_t total_bytes;
+  // NB200_BF16X3 (error-compensated bf16, forward only): its own packed buffer = per K-block a hi slab bf16(W) and a lo
+  // slab bf16(W - bf16(W)), then the same fp32 tail
+  int num_fwd3;
+  SlabDesc fwd3[2 * kMaxSlabs];
+  uint32_t f32_off3;
+  uint32_t total_bytes3;
 };
 constexpr int kF32Bias = 0, kF32WSig = 2560, kF32BSig = 2816, kF32WC1 = 2820, kF32BC1 = 3204,
               kF32Floats = 3264;
@@ -60,7 +69,7 @@ static bool h_layout_built = false;
 // Everything CUDA caches per device (constant-bank copies, function attributes, the architecture check) is keyed
 // by the current device, so one process can drive several GPUs; the tables are guarded by one mutex.
 constexpr int kMaxDevices = 64;
-struct DeviceState { bool layout_uploaded, attr_fwd, attr_render, attr_bwd; int arch; };
+struct DeviceState { bool layout_uploaded, attr_fwd, attr_render, attr_bwd, attr_x3; int arch; };
 static DeviceState g_dev[kMaxDevices];
 static std::mutex g_mu;
 static int current_device(int* dev) {
@@ -76,8 +85,10 @@ struct LayoutBuilder {
   SlabDesc* arr;
   uint32_t off;
   int s;
-  void add(int ml, int layer, int transposed, int n, int wcol0, int kvalid, int ldw, int src, int kb, int ksteps) {
+  void add(int ml, int layer, int transposed, int n, int wcol0, int kvalid, int ldw, int src, int kb, int ksteps, int lo = 0,
+           int amode = 0) {
     SlabDesc& d = arr[s++];
+    d.lo = (uint8_t)lo; d.amode = (uint8_t)amode; d.pad[0] = d.pad[1] = 0;
     d.off = off; d.bytes = (uint32_t)n * 128u; d.n = (uint16_t)n; d.wcol0 = (uint16_t)wcol0;
     d.kvalid = (uint16_t)kvalid; d.ldw = (uint16_t)ldw; d.ml = (uint8_t)ml; d.layer = (uint8_t)layer;
     d.src = (uint8_t)src; d.kb = (uint8_t)kb; d.ksteps = (uint8_t)ksteps; d.first = 0; d.last = 0;
@@ -127,6 +138,20 @@ static void build_layout() {
   h_layout.num_bwd = t.s;
   h_layout.f32_off = t.off;
   h_layout.total_bytes = t.off + kF32Floats * (uint32_t)sizeof(float);
+  // bf16x3: every forward slab twice (hi: consumed with A_hi and A_lo; lo: with A_hi), in consumption order
+  LayoutBuilder x;
+  x.arr = h_layout.fwd3; x.off = 0; x.s = 0;
+  for (int i = 0; i < h_layout.num_fwd; ++i) {
+    const SlabDesc& f = h_layout.fwd[i];
+    for (int lo = 0; lo < 2; ++lo) {
+      x.add(f.ml, f.layer, 0, f.n, f.wcol0, f.kvalid, f.ldw, f.src, f.kb, f.ksteps, lo, lo ? 0 : 1);
+      h_layout.fwd3[x.s - 1].first = (uint8_t)(f.first && lo == 0);
+      h_layout.fwd3[x.s - 1].last = (uint8_t)(f.last && lo == 1);
+    }
+  }
+  h_layout.num_fwd3 = x.s;
+  h_layout.f32_off3 = x.off;
+  h_layout.total_bytes3 = x.off + kF32Floats * (uint32_t)sizeof(float);
 }
 
 static void ensure_host_layout() {   // caller holds g_mu
@@ -148,10 +173,10 @@ struct ParamPtrs { const float* p[24]; };
 // kPackSplit blocks per slab: fp32 weight -> bf16 SWIZZLE_128B operand image [n rows x 64 k-columns].
 // (It runs once per optimizer step; one block per slab left half of the SMs idle: 12.5 us.)
 constexpr int kPackSplit = 4;
-__global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
+__global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed, int x3) {
   const int slab = (int)blockIdx.x / kPackSplit, part = (int)blockIdx.x % kPackSplit;
-  const bool is_bwd = slab >= c_layout.num_fwd;
-  const SlabDesc d = is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab];
+  const bool is_bwd = !x3 && slab >= c_layout.num_fwd;
+  const SlabDesc d = x3 ? c_layout.fwd3[slab] : (is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab]);
   const float* W = P.p[2 * d.layer];
   for (int item = part * blockDim.x + threadIdx.x; item < d.n * 8; item += blockDim.x * kPackSplit) {
     const int n = item >> 3, j = item & 7;
@@ -165,6 +190,7 @@ __global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* _
         v[h] = 0.f;
         if (k < d.kvalid)
           v[h] = d.transposed ? __ldg(W + (size_t)(d.wcol0 + k) * d.ldw + n) : __ldg(W + (size_t)n * d.ldw + d.wcol0 + k);
+        if (d.lo) v[h] -= __bfloat162float(__float2bfloat16_rn(v[h]));   // residual of the hi image
       }
       w[e] = pack_bf16x2(v[0], v[1]);
     }
@@ -257,10 +283,10 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
 #include "mlp_chain.cuh"
 
 // ------------------------------------------------------------------------------ host API
-size_t tc_packed_bytes() {
+size_t tc_packed_bytes(int x3) {
   std::lock_guard<std::mutex> lock(g_mu);
   ensure_host_layout();  // layout is host-computable without a device
-  return h_layout.total_bytes;
+  return x3 ? h_layout.total_bytes3 : h_layout.total_bytes;
 }
 // Training tensors are laid out for an EVEN number of 128-sample tiles: the chain kernels work on pair-tiles
 // (one tile per CTA of a cluster), so with an odd tile count the second CTA of the last pair still writes a
@@ -290,14 +316,15 @@ __global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict_
   if (c < ncols) g[(size_t)r * ncols + c] += pad[i];
 }
 
-int tc_pack_weights(const float* const* P, void* packed, cudaStream_t s) {
+int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s) {
   NB_TRY_RC(ensure_layout());
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = P[i];
-  pack_slabs_kernel<<<(h_layout.num_fwd + h_layout.num_bwd) * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
+  const int nslabs = x3 ? h_layout.num_fwd3 : h_layout.num_fwd + h_layout.num_bwd;
+  pack_slabs_kernel<<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed), x3);
   NB_LAUNCH_CHECK("pack_slabs_kernel");
   pack_f32_kernel<<<(kF32Floats + 255) / 256, 256, 0, s>>>(
-      pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + h_layout.f32_off));
+      pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + (x3 ? h_layout.f32_off3 : h_layout.f32_off)));
   NB_LAUNCH_CHECK("pack_f32_kernel");
   return NB200_OK;
 }
@@ -334,7 +361,7 @@ static int ensure_attr(bool DeviceState::*which, F&& set) {
 struct ConstSlotEntry { const void* packed; int dev; };
 static ConstSlotEntry g_slots[kConstSlots];
 static int g_slot_next = 0;
-static int upload_consts(const void* packed, cudaStream_t s, int* slot_out) {
+static int upload_consts(const void* packed, cudaStream_t s, int* slot_out, int x3 = 0) {
   int dev = 0;
   NB_TRY_RC(current_device(&dev));
   int slot = -1;
@@ -348,7 +375,7 @@ static int upload_consts(const void* packed, cudaStream_t s, int* slot_out) {
       g_slots[slot].packed = packed; g_slots[slot].dev = dev;
     }
   }
-  NB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_f32, reinterpret_cast<const uint8_t*>(packed) + h_layout.f32_off,
+  NB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_f32, reinterpret_cast<const uint8_t*>(packed) + (x3 ? h_layout.f32_off3 : h_layout.f32_off),
                                         kF32Floats * sizeof(float), (size_t)slot * kF32Floats * sizeof(float),
                                         cudaMemcpyDeviceToDevice, s));
   *slot_out = slot;
@@ -362,7 +389,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 struct TmapPair { const void* packed; int dev; CUtensorMap m128, m64; };
-static int get_tmaps(const void* packed, TmapPair* out) {   // returns a COPY: the cache entry may be recycled by another thread
+static int get_tmaps(const void* packed, TmapPair* out, int x3 = 0) {   // returns a COPY: the cache entry may be recycled by another thread
   int dev = 0;
   NB_TRY_RC(current_device(&dev));
   std::lock_guard<std::mutex> lock(g_mu);
@@ -382,7 +409,7 @@ static int get_tmaps(const void* packed, TmapPair* out) {   // returns a COPY: t
   next = (next + 1) % 8;
   if (used < 8) ++used;
   t.packed = nullptr;
-  const cuuint64_t gdim[2] = {64, (cuuint64_t)(h_layout.f32_off / 128)};
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)((x3 ? h_layout.f32_off3 : h_layout.f32_off) / 128)};
   const cuuint64_t gstride[1] = {128};
   const cuuint32_t estride[2] = {1, 1};
   for (int k = 0; k < 2; ++k) {
@@ -451,6 +478,35 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   else
     chain_kernel<FwdEpi<false>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
   NB_LAUNCH_CHECK("chain_kernel<FwdEpi>");
+  return NB200_OK;
+}
+
+// NB200_BF16X3: error-compensated bf16 on the same chain skeleton (one tile in flight per CTA, three MMA passes per
+// K-block: A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation in TMEM): fp32-class accuracy on the tensor cores.
+int tc_forward_x3(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed, float* out,
+                  cudaStream_t s) {
+  NB_TRY_RC(check_arch());
+  NB_TRY_RC(ensure_layout());
+  NB_TRY_RC(ensure_attr(&DeviceState::attr_x3, []() -> int {
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
+    return NB200_OK;
+  }));
+  const int64_t T = ceil_div64(M, kTileM);
+  FwdEpiParams p;
+  memset(&p, 0, sizeof(p));
+  NB_TRY_RC(upload_consts(packed, s, &p.cslot, 1));
+  TmapPair tm;
+  NB_TRY_RC(get_tmaps(packed, &tm, 1));
+  p.tmap128 = tm.m128; p.tmap64 = tm.m64;
+  p.in_mode = in_mode; p.in0 = in0; p.in1 = in1; p.M = M; p.N = N;
+  p.nshift = (N > 0 && (N & (N - 1)) == 0) ? __builtin_ctz((unsigned)N) : -1;
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
+  p.out = out;
+  p.num_tiles = T;
+  const int64_t PT = (T + 1) / 2, maxc = sm_count() / 2;
+  const int grid = (int)(2 * (PT < maxc ? PT : maxc));
+  chain_kernel<FwdEpi3><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
+  NB_LAUNCH_CHECK("chain_kernel<FwdEpi3>");
   return NB200_OK;
 }
 

@@ -14,7 +14,7 @@ import torch
 from . import _lib, config
 
 NUM_PARAMS = 595844
-_PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16}
+_PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16, "bf16x3": _lib.BF16X3}
 
 
 def flat_views(flat, shapes):
@@ -55,29 +55,29 @@ class PackedWeights:
     masters in place between calls, train.py:55)."""
 
     def __init__(self):
-        self.buf = None
-        self.key = None
+        self.bufs = {}      # precision -> (key, buffer): bf16 and bf16x3 images have different layouts
 
     def invalidate(self):
         """Force a re-pack on the next call.  Needed after writes the version counters do not see: `p.data.copy_()`,
         `p.data.normal_()`, EMA swaps through `.data` (in-place ops on the parameter itself, `optimizer.step()` and
         `load_state_dict` bump the version and need nothing)."""
-        self.key = None
+        self.bufs = {p: (None, b) for p, (_, b) in self.bufs.items()}
 
     def get(self, params, precision):
         if precision == _lib.FP32:
             return None
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self.buf is None or self.key != key or self.buf.device != params[0].device:
+        old_key, buf = self.bufs.get(precision, (None, None))
+        if buf is None or old_key != key or buf.device != params[0].device:
             lib = _lib.load()
             nbytes = lib.nb200_packed_weights_bytes(precision)
-            if self.buf is None or self.buf.device != params[0].device:
-                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
-            rc = lib.nb200_pack_weights(precision, _lib.ptr_array(params), _lib.ptr(self.buf),
+            if buf is None or buf.device != params[0].device:
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+            rc = lib.nb200_pack_weights(precision, _lib.ptr_array(params), _lib.ptr(buf),
                                         _lib.stream_ptr(params[0].device))
             _lib.check(rc, "nb200_pack_weights")
-            self.key = key
-        return self.buf
+            self.bufs[precision] = (key, buf)
+        return buf
 
 
 class _MLPFunction(torch.autograd.Function):
@@ -90,7 +90,7 @@ class _MLPFunction(torch.autograd.Function):
         saved = None
         if need_grad:
             saved = torch.empty(lib.nb200_mlp_saved_bytes(precision, M), dtype=torch.uint8, device=dev)
-        sb = lib.nb200_mlp_scratch_bytes(precision, M, 0) if not need_grad or precision == _lib.BF16 else 0
+        sb = lib.nb200_mlp_scratch_bytes(precision, M, 0) if not need_grad or precision != _lib.FP32 else 0
         scratch = torch.empty(sb, dtype=torch.uint8, device=dev) if sb else None
         rc = lib.nb200_mlp_forward(precision, in_mode, _lib.ptr(in0), _lib.ptr(in1), M, N,
                                    _lib.ptr_array(params), _lib.ptr(packed), _lib.ptr(out),
@@ -132,11 +132,13 @@ def mlp_apply(net, in_mode, in0, in1=None, N=1, precision=None):
     in0 = _f32c(in0, "input")
     if in_mode == _lib.IN_RAYS:
         in1 = _f32c(in1, "ts")
-    packed = net._packed.get(params, precision)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if need_grad and precision == _lib.BF16X3:
+        precision = _lib.FP32      # bf16x3 is a forward mode: gradients in fp32-class accuracy come from the fp32 kernels
+    packed = net._packed.get(params, precision)
     cap = config._state["max_samples_per_call"]
     M = in0.shape[0] if in_mode == _lib.IN_POINTS else in0.shape[0] * N
-    if need_grad or M <= cap or precision == _lib.BF16:
+    if need_grad or M <= cap or precision != _lib.FP32:
         return _MLPFunction.apply(precision, in_mode, N, need_grad, packed, in0, in1, *params)
     # inference in fp32 parity mode: bound the per-call activation workspace
     step = max(1, cap // N) if in_mode == _lib.IN_RAYS else cap

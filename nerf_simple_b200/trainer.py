@@ -368,4 +368,4 @@ class Trainer:
 
     def _bump_versions(self):
         # the optimizer updated the flat buffer, not the 24 views: invalidate the packed-weight cache
-        self.net._packed.key = None
+        self.net._packed.invalidate()

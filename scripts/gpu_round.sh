@@ -15,6 +15,7 @@ for st in $stages; do
     sanitize)
       for tool in memcheck racecheck; do timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_stream_kernels.py > $out/${tag}_sanitizer_${tool}_stream.log 2>&1; tail -2 $out/${tag}_sanitizer_${tool}_stream.log; done
       timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_chain_kernels.py > $out/${tag}_sanitizer_memcheck_chain.log 2>&1; tail -3 $out/${tag}_sanitizer_memcheck_chain.log ;;
+    parity) timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -s > $out/${tag}_parity.log 2>&1; echo "parity rc=$?"; grep -i 'x1.5\|passed\|failed\|Error' $out/${tag}_parity.log | tail -8 ;;
     smoke)  timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $out/${tag}_smoke.log ;;
     ncu_launch)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_train.csv python bench.py --workload train --steps 3 --warmup 3 > $out/${tag}_ncu_train.log 2>&1

@@ -9,7 +9,7 @@ from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "bf16": 1e-2}        # BASELINE.json north_star tolerances (max abs err)
+TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16x3": 1e-4}        # BASELINE.json north_star tolerances (max abs err); bf16x3 = tensor-core fp32-class mode
 
 
 def maxabs(a, b):
@@ -26,7 +26,7 @@ def net(golden_weights):
     return n
 
 
-@pytest.fixture(params=["fp32", "bf16"])
+@pytest.fixture(params=["fp32", "bf16", "bf16x3"])
 def precision(request):
     from nerf_simple_b200 import config
     config.set_precision(request.param)
@@ -150,6 +150,29 @@ def test_mlp_forward_points(net, precision, golden_weights):
     assert maxabs(out, g["out"][:1037]) <= TOL[precision]
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_fp32_class_modes_hold_1e4_with_scaled_weights(golden_weights, prec):
+    """single-pass TF32 passes 1e-4 only barely at default init and FAILS (2.7e-4) with the weights
+    scaled x1.5.  Both fp32-class modes -- the SIMT kernels and the error-compensated bf16 tensor-core kernel -- must
+    hold 1e-4 there too (reference = the numpy oracle evaluated in float64)."""
+    from nerf_simple_b200 import config
+    from nerf_simple_b200.nets import Nerf
+    g = load_golden("case_train_b64_n64.npz")
+    P = {k: (v * 1.5).astype(np.float32) for k, v in golden_weights.items()}
+    n = Nerf().cuda()
+    n.load_state_dict({k: torch.from_numpy(v) for k, v in P.items()}, strict=True)
+    ref = O.mlp_forward(g["query"], P, dtype=np.float64)
+    config.set_precision(prec)
+    try:
+        with torch.no_grad():
+            out = n(torch.from_numpy(g["query"]).cuda())
+    finally:
+        config.set_precision("bf16")
+    err = maxabs(out, ref)
+    print(f"weights x1.5 [{prec}]: max abs err {err:.3e} (outputs up to {np.abs(ref).max():.2f})")
+    assert err <= 1e-4
+
+
 @pytest.mark.parametrize("case,N", [("case_train_b64_n64.npz", 64), ("case_render_b1024_n64.npz", 64),
                                     ("case_all5_b96_n128.npz", 128)])
 def test_render_nerf_forward(net, precision, case, N):
@@ -189,16 +212,16 @@ def test_train_step_gradients(net, precision):
     rgb, *_ = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 64)
     loss = torch.nn.MSELoss()(rgb, torch.from_numpy(g["gt"]).cuda())
     loss.backward()
-    assert abs(loss.item() - float(g["loss"])) <= (1e-5 if precision == "fp32" else 2e-3)
+    assert abs(loss.item() - float(g["loss"])) <= (1e-5 if precision != "bf16" else 2e-3)
     _grad_check(net, {k[5:]: v for k, v in g.items() if k.startswith("grad.")},
-                2e-3 if precision == "fp32" else 5e-2)
+                2e-3 if precision != "bf16" else 5e-2)      # (bf16x3: forward on the tensor cores, gradients from the fp32 kernels)
     # gradients accumulate across backward calls like autograd
     g1 = [p.grad.clone() for p in net.parameters()]
     torch.manual_seed(1)
     rgb, *_ = render_nerf(torch.from_numpy(g["rays"]).cuda(), net, 64)
     torch.nn.MSELoss()(rgb, torch.from_numpy(g["gt"]).cuda()).backward()
     for a, p in zip(g1, net.parameters()):
-        assert torch.allclose(p.grad, 2 * a, rtol=1e-3 if precision == "fp32" else 5e-2, atol=1e-7)
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-3 if precision != "bf16" else 5e-2, atol=1e-7)
 
 
 def test_all_five_outputs_gradient(net, precision):
@@ -219,7 +242,7 @@ def test_all_five_outputs_gradient(net, precision):
             # tensor's max elementwise and 15% in relative L2 norm (worst tensor: layers_0.0.weight, whose
             # delta went through nine bf16 roundings; the well-conditioned train-step case is held to 5e-2).
             err = maxabs(p.grad, grads[k])
-            if precision == "fp32":
+            if precision != "bf16":
                 assert err <= 3e-2 * scale, k
             else:
                 l2 = float(np.linalg.norm(p.grad.cpu().numpy() - grads[k]) / max(1e-12, np.linalg.norm(grads[k])))
@@ -249,7 +272,7 @@ def test_full_size_properties(net, precision):
     with torch.no_grad():
         full = ops.mlp_apply(net, _lib.IN_RAYS, rays, ts, 64)
         part = ops.mlp_apply(net, _lib.IN_RAYS, rays[1000:1500], ts[1000:1500], 64)
-    assert maxabs(full.view(4096, 64, 4)[1000:1500].reshape(-1, 4), part) <= (1e-6 if precision == "fp32" else 1e-6)
+    assert maxabs(full.view(4096, 64, 4)[1000:1500].reshape(-1, 4), part) <= 1e-6
 
 
 def test_render_image_and_poses_shapes(net, precision, tmp_path):
