@@ -30,7 +30,7 @@ constexpr int kCProducerWarp = 16, kCMmaWarp = 17, kCStoreWarp0 = 18;
 constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128, kB_Written = 136,
                    kB_StoreFree = 152;
 
-__constant__ float c_f32[kConstSlots * kF32Floats];  // biases / head weights of the nets being run (slot per packed buffer, uploaded per call)
+__constant__ __align__(16) float c_f32[kConstSlots * kF32Floats];  // biases / head weights of the nets being run (slot per packed buffer, uploaded per call)
 
 struct TileCtx {
   int64_t tile;      // 128-row tile index
@@ -242,7 +242,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
                 umma_bf16_2cta(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
                 umma_bf16_2cta(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
               }
-              if (Epi::kSplit3 && slabs[s].amode) {   // bf16x3: the same B slab against the residual image A_lo (the other slot's buffer)
+              if (Epi::kSplit3 && (slabs[s].flags & kSlabBothA)) {   // bf16x3: the same B slab against the residual image A_lo (the other slot's buffer)
                 const uint64_t alo = adesc + ((slabs[s].src ? kEBytes : kABytes) >> 4);
                 umma_bf16_2cta(d_tmem, alo, bdesc, idesc, 1u);
                 umma_bf16_2cta(d_tmem, alo + 2, bdesc + 2, idesc, 1u);

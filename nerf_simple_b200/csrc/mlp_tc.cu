@@ -38,11 +38,13 @@ struct SlabDesc {
   uint8_t ksteps;   // number of K=16 MMAs
   uint8_t first;    // first slab of its layer (accumulator is overwritten)
   uint8_t last;     // last slab of its layer (commit to acc_full)
-  uint8_t transposed;  // image(n,k) = W[(wcol0+k)*ldw + n] (dgrad operand) instead of W[n*ldw + wcol0+k]
-  uint8_t lo;          // bf16x3 mode: image of the residual W - bf16(W) instead of bf16(W)
-  uint8_t amode;       // bf16x3 mode: 1 = this slab multiplies A_hi and then A_lo, 0 = A_hi only
-  uint8_t pad[2];
+  uint8_t flags;    // kSlabTransposed | kSlabLo | kSlabBothA (the struct stays 24 bytes: the MMA warp's issue loop reads it
+                    // through the uniform datapath, and a 28-byte stride cost the forward kernel 13 %)
 };
+constexpr uint8_t kSlabTransposed = 1;  // image(n,k) = W[(wcol0+k)*ldw + n] (dgrad operand) instead of W[n*ldw + wcol0+k]
+constexpr uint8_t kSlabLo = 2;          // bf16x3: image of the residual W - bf16(W) instead of bf16(W)
+constexpr uint8_t kSlabBothA = 4;       // bf16x3: this slab multiplies A_hi and then A_lo (else A_hi only)
+static_assert(sizeof(SlabDesc) == 24, "SlabDesc layout");
 
 struct PackedLayout {
   int num_fwd;
@@ -62,7 +64,7 @@ constexpr int kF32Bias = 0, kF32WSig = 2560, kF32BSig = 2816, kF32WC1 = 2820, kF
               kF32Floats = 3264;
 constexpr int kConstSlots = 4;   // constant-bank copies of the fp32 tail (4 x 13 KB): concurrent nets never share one
 
-__constant__ PackedLayout c_layout;
+__constant__ __align__(16) PackedLayout c_layout;
 static PackedLayout h_layout;
 static bool h_layout_built = false;
 
@@ -88,11 +90,10 @@ struct LayoutBuilder {
   void add(int ml, int layer, int transposed, int n, int wcol0, int kvalid, int ldw, int src, int kb, int ksteps, int lo = 0,
            int amode = 0) {
     SlabDesc& d = arr[s++];
-    d.lo = (uint8_t)lo; d.amode = (uint8_t)amode; d.pad[0] = d.pad[1] = 0;
     d.off = off; d.bytes = (uint32_t)n * 128u; d.n = (uint16_t)n; d.wcol0 = (uint16_t)wcol0;
     d.kvalid = (uint16_t)kvalid; d.ldw = (uint16_t)ldw; d.ml = (uint8_t)ml; d.layer = (uint8_t)layer;
     d.src = (uint8_t)src; d.kb = (uint8_t)kb; d.ksteps = (uint8_t)ksteps; d.first = 0; d.last = 0;
-    d.transposed = (uint8_t)transposed;
+    d.flags = (uint8_t)((transposed ? kSlabTransposed : 0) | (lo ? kSlabLo : 0) | (amode ? kSlabBothA : 0));
     off += d.bytes;
   }
 };
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* _
         const int k = j * 8 + 2 * e + h;
         v[h] = 0.f;
         if (k < d.kvalid)
-          v[h] = d.transposed ? __ldg(W + (size_t)(d.wcol0 + k) * d.ldw + n) : __ldg(W + (size_t)n * d.ldw + d.wcol0 + k);
-        if (d.lo) v[h] -= __bfloat162float(__float2bfloat16_rn(v[h]));   // residual of the hi image
+          v[h] = (d.flags & kSlabTransposed) ? __ldg(W + (size_t)(d.wcol0 + k) * d.ldw + n) : __ldg(W + (size_t)n * d.ldw + d.wcol0 + k);
+        if (d.flags & kSlabLo) v[h] -= __bfloat162float(__float2bfloat16_rn(v[h]));   // residual of the hi image
       }
       w[e] = pack_bf16x2(v[0], v[1]);
     }
@@ -388,15 +389,17 @@ static int upload_consts(const void* packed, cudaStream_t s, int* slot_out, int 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-struct TmapPair { const void* packed; int dev; CUtensorMap m128, m64; };
+struct TmapPair { const void* packed; int dev; uint32_t rows; CUtensorMap m128, m64; };
 static int get_tmaps(const void* packed, TmapPair* out, int x3 = 0) {   // returns a COPY: the cache entry may be recycled by another thread
   int dev = 0;
   NB_TRY_RC(current_device(&dev));
   std::lock_guard<std::mutex> lock(g_mu);
   static TmapPair cache[8];
   static int used = 0, next = 0;
+  // keyed by the image's row count too: torch's allocator hands a freed bf16 buffer's address to a bf16x3 buffer
+  const uint32_t rows = (x3 ? h_layout.f32_off3 : h_layout.f32_off) / 128;
   for (int i = 0; i < used; ++i)
-    if (cache[i].packed == packed && cache[i].dev == dev) { *out = cache[i]; return NB200_OK; }
+    if (cache[i].packed == packed && cache[i].dev == dev && cache[i].rows == rows) { *out = cache[i]; return NB200_OK; }
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -409,7 +412,7 @@ static int get_tmaps(const void* packed, TmapPair* out, int x3 = 0) {   // retur
   next = (next + 1) % 8;
   if (used < 8) ++used;
   t.packed = nullptr;
-  const cuuint64_t gdim[2] = {64, (cuuint64_t)((x3 ? h_layout.f32_off3 : h_layout.f32_off) / 128)};
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {128};
   const cuuint32_t estride[2] = {1, 1};
   for (int k = 0; k < 2; ++k) {
@@ -424,6 +427,7 @@ static int get_tmaps(const void* packed, TmapPair* out, int x3 = 0) {   // retur
   }
   t.packed = packed;
   t.dev = dev;
+  t.rows = rows;
   *out = t;
   return NB200_OK;
 }
