@@ -141,6 +141,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         reclaim();
         Epi::layer(p, st, c, l);
         if (Epi::kBulkStore || l + 1 < Epi::kNumLayers) publish(l + 1 < Epi::kNumLayers);
+        Epi::after_publish(p, c, l);
       }
     }
     if (Epi::kBulkStore && !first_step) mbar_wait(bar + kB_StoreFree + 8 * slot, free_parity, 501);   // last store read its image
@@ -415,8 +416,7 @@ __device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint
 // thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
 // (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, uint32_t& mflags,
-                                           float& sigma) {
+__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, float& sigma) {
   const float* b = c.cf + bias_off + col0;
   const float* ws = c.cf + kF32WSig + col0;
   const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
@@ -436,10 +436,6 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
     if (kRelu) {
       w0 = pack_bf16x2_relu(x[0], x[1]); w1 = pack_bf16x2_relu(x[2], x[3]);
       w2 = pack_bf16x2_relu(x[4], x[5]); w3 = pack_bf16x2_relu(x[6], x[7]);
-      if (kSave) {  // ReLU bit mask of the saved (bf16) activation, read by the delta chain
-        add_pair_flags(mflags, w0, 4 * j); add_pair_flags(mflags, w1, 4 * j + 1);
-        add_pair_flags(mflags, w2, 4 * j + 2); add_pair_flags(mflags, w3, 4 * j + 3);
-      }
     } else {
       w0 = pack_bf16x2(x[0], x[1]); w1 = pack_bf16x2(x[2], x[3]);
       w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
@@ -455,21 +451,18 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 // fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), biases come from the constant bank and are
 // added two at a time (add.f32x2).
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, uint8_t* gmask, float& sigma) {
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float& sigma) {
   const int cbase = c.half * 128;
   uint32_t a0[16], a1[16];
   tmem_ld16(c.t_lane + cbase, a0);
 #pragma unroll 1
   for (int q = 0; q < 8; q += 2) {
-    uint32_t f0 = 0u, f1 = 0u;
     tmem_ld_wait();                                       // a0 (step q) has landed
     tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);       // step q+1 in flight
-    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, f0, sigma);
+    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, sigma);
     tmem_ld_wait();                                       // a1 has landed
     if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
-    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, f1, sigma);
-    if (kSave && kRelu)  // 32 columns = one word of this thread's 16-byte mask row (a warp writes 32 rows x 4 B, 16 B apart)
-      *reinterpret_cast<uint32_t*>(gmask + ((size_t)(c.half * 128) + c.r) * 16 + (q >> 1) * 4) = fold_mask16(f0) | (fold_mask16(f1) << 16);
+    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, sigma);
   }
 }
 
@@ -493,6 +486,46 @@ struct FwdEpi {
   __device__ static const SlabDesc* slabs() { return c_layout.fwd; }
 
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
+
+  // Training: the ReLU bit masks the delta chain reads (one bit per element of h0..h7 and c1) are formed AFTER the tile
+  // image was handed to the MMA warp and the store warp, from the bf16 image in shared memory: the epilogue warps of
+  // this slot would otherwise idle until their next accumulator is ready, so the ~130 extra instructions per thread
+  // and layer stay off the critical path (inside the epilogue they cost the kernel 11 %).
+  __device__ static void after_publish(const Params& p, const TileCtx& c, int ml) {
+    if (!kSave || ml < 0 || ml == 8) return;
+    const int64_t T = p.num_tiles;
+    if (ml < 8) {
+      uint8_t* row = p.saved + mask_tensor_off(ml, T) + (size_t)c.tile * 4096 + ((size_t)(c.half * 128) + c.r) * 16;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {          // 32 columns = 4 chunks of 16 B = one mask word
+        const uint32_t kb = (uint32_t)(c.half * 2 + (q >> 1)), j0 = (uint32_t)(q & 1) * 4u;
+        uint32_t f[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(c.a_img + sw_off(c, kb, j0 + j)));
+          add_pair_flags(f[j >> 1], w0, 4 * (j & 1)); add_pair_flags(f[j >> 1], w1, 4 * (j & 1) + 1);
+          add_pair_flags(f[j >> 1], w2, 4 * (j & 1) + 2); add_pair_flags(f[j >> 1], w3, 4 * (j & 1) + 3);
+        }
+        *reinterpret_cast<uint32_t*>(row + q * 4) = fold_mask16(f[0]) | (fold_mask16(f[1]) << 16);
+      }
+    } else {   // ml == 9: c1, 64 columns per thread = K-block `half` of the image
+      uint8_t* row = p.saved + mask_tensor_off(8, T) + (size_t)c.tile * 2048 + ((size_t)(c.half * 128) + c.r) * 8;
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t f[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(c.a_img + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j))));
+          add_pair_flags(f[j >> 1], w0, 4 * (j & 1)); add_pair_flags(f[j >> 1], w1, 4 * (j & 1) + 1);
+          add_pair_flags(f[j >> 1], w2, 4 * (j & 1) + 2); add_pair_flags(f[j >> 1], w3, 4 * (j & 1) + 3);
+        }
+        *reinterpret_cast<uint32_t*>(row + q * 4) = fold_mask16(f[0]) | (fold_mask16(f[1]) << 16);
+      }
+    }
+  }
 
   __device__ static void begin_tile(const Params& p, State& st, const TileCtx& c) {
     st.m_raw = c.tile * kTileM + c.r;
@@ -521,10 +554,9 @@ struct FwdEpi {
       else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, nullptr);
     }
     if (ml < 9) {
-      uint8_t* gmask = (kSave && ml < 8) ? p.saved + mask_tensor_off(ml, T) + (size_t)c.tile * 4096 : nullptr;
-      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);
-      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);  // layers_2: no act.
-      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, gmask, st.sigma);
+      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, st.sigma);
+      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, st.sigma);  // layers_2: no act.
+      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, st.sigma);
     } else {
       // color_fc.0 epilogue (128 columns, ReLU; this thread's half = 64 of them) + color_fc.2
       // (128 -> 3) on CUDA cores; the two halves of a row meet through the (now free) E buffer
@@ -532,7 +564,6 @@ struct FwdEpi {
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
         const int col0 = c.half * 64 + q * 32;
-        uint32_t f0 = 0u, f1 = 0u;
         uint32_t a[32];
         tmem_ld32(c.t_lane + col0, a);
         tmem_ld_wait();
@@ -552,14 +583,8 @@ struct FwdEpi {
             const uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
                            w3 = pack_bf16x2(x[6], x[7]);
             st_shared_v4(c.a_img + sw_off(c, (uint32_t)c.half, (uint32_t)(q * 4 + j)), w0, w1, w2, w3);
-            uint32_t& f = (j < 2) ? f0 : f1;      // 16-column steps: j = 0,1 and j = 2,3
-            add_pair_flags(f, w0, 4 * (j & 1)); add_pair_flags(f, w1, 4 * (j & 1) + 1);
-            add_pair_flags(f, w2, 4 * (j & 1) + 2); add_pair_flags(f, w3, 4 * (j & 1) + 3);
           }
         }
-        if (kSave)  // this thread's 64 columns of c1: 8-byte mask row, one word per 32 columns
-          *reinterpret_cast<uint32_t*>(p.saved + mask_tensor_off(8, T) + (size_t)c.tile * 2048 + ((size_t)(c.half * 128) + c.r) * 8 + q * 4) =
-              fold_mask16(f0) | (fold_mask16(f1) << 16);
       }
       const uint32_t xaddr = c.e_img + c.r * 16u;
       if (c.half == 1) st_shared_v4(xaddr, __float_as_uint(rgb[0]), __float_as_uint(rgb[1]), __float_as_uint(rgb[2]), __float_as_uint(st.sigma));
@@ -647,6 +672,7 @@ struct FwdEpi3 {
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd3; }
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
+  __device__ static void after_publish(const Params&, const TileCtx&, int) {}
   __device__ static void store_tile(const Params&, const TileCtx&, int) {}
 
   __device__ static void encode(const float* x, const TileCtx& c, bool dirs) {
@@ -756,6 +782,7 @@ struct DgradEpi {
   static constexpr bool kReverseTiles = true;
   struct State { float4 g; uint4 mask; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
+  __device__ static void after_publish(const Params&, const TileCtx&, int) {}
 
   // The ReLU mask of layer l is this thread's 16-byte row of the bit-mask tensor the forward pass wrote (one bit per
   // element instead of the 64 KB bf16 activation tile): ONE load per thread and layer, issued before the accumulator
