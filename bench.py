@@ -485,7 +485,7 @@ def bench_train(args, c, B, N, steps, warmup, loop_api=False):
     pk = load_peaks()
     M = B * N
     achieved = FLOP_TRAIN * M / (ms_step * 1e-3) / 1e12
-    traffic, tsrc = load_traffic("train_step_backward") if (B, N) == (4096, 64) else (None, None)
+    traffic, tsrc = load_traffic("train_step_mlp_kernels") if (B, N) == (4096, 64) else (None, None)
     rec = {"metric": "rays/sec (64 samples/ray) train", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": ms_step, "scaling": "weak", "dtype": args.precision, "samples_per_sec": value * N,
            "config": {"workload": f"training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, fused compositing backward "

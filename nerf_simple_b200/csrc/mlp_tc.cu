@@ -174,10 +174,11 @@ struct ParamPtrs { const float* p[24]; };
 // kPackSplit blocks per slab: fp32 weight -> bf16 SWIZZLE_128B operand image [n rows x 64 k-columns].
 // (It runs once per optimizer step; one block per slab left half of the SMs idle: 12.5 us.)
 constexpr int kPackSplit = 4;
-__global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed, int x3) {
+template <bool kX3>
+__global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
   const int slab = (int)blockIdx.x / kPackSplit, part = (int)blockIdx.x % kPackSplit;
-  const bool is_bwd = !x3 && slab >= c_layout.num_fwd;
-  const SlabDesc d = x3 ? c_layout.fwd3[slab] : (is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab]);
+  const bool is_bwd = !kX3 && slab >= c_layout.num_fwd;
+  const SlabDesc d = kX3 ? c_layout.fwd3[slab] : (is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab]);
   const float* W = P.p[2 * d.layer];
   for (int item = part * blockDim.x + threadIdx.x; item < d.n * 8; item += blockDim.x * kPackSplit) {
     const int n = item >> 3, j = item & 7;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* _
         v[h] = 0.f;
         if (k < d.kvalid)
           v[h] = (d.flags & kSlabTransposed) ? __ldg(W + (size_t)(d.wcol0 + k) * d.ldw + n) : __ldg(W + (size_t)n * d.ldw + d.wcol0 + k);
-        if (d.flags & kSlabLo) v[h] -= __bfloat162float(__float2bfloat16_rn(v[h]));   // residual of the hi image
+        if (kX3 && (d.flags & kSlabLo)) v[h] -= __bfloat162float(__float2bfloat16_rn(v[h]));   // residual of the hi image
       }
       w[e] = pack_bf16x2(v[0], v[1]);
     }
@@ -322,7 +323,8 @@ int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s)
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = P[i];
   const int nslabs = x3 ? h_layout.num_fwd3 : h_layout.num_fwd + h_layout.num_bwd;
-  pack_slabs_kernel<<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed), x3);
+  if (x3) pack_slabs_kernel<true><<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
+  else pack_slabs_kernel<false><<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
   NB_LAUNCH_CHECK("pack_slabs_kernel");
   pack_f32_kernel<<<(kF32Floats + 255) / 256, 256, 0, s>>>(
       pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + (x3 ? h_layout.f32_off3 : h_layout.f32_off)));
