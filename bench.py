@@ -491,7 +491,10 @@ def bench_train(args, c, B, N, steps, warmup, loop_api=False):
            "config": {"workload": f"training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, fused compositing backward "
                                   f"(train.py:47-57)", "rays_table": "25 views 400x400 (4.0 M rays) on device",
                       "parallelism": f"data-parallel over {world} rank(s), one all-reduce of 595,844 fp32 grads/step",
-                      "launch": launch_mode, "l2": f"saved activations + deltas per step = {M * 10e3 / 1e9:.1f} GB (larger than L2)"},
+                      "launch": launch_mode,
+                      "limiter": "HBM bytes of saved activations + deltas (5.5 GB per 4096x64 step, profiles/traffic.json) under the 1 kW power "
+                                 "cap; the data-parallel all-reduce is fused into the Adam kernel (no collective in the step)",
+                      "l2": f"saved activations + deltas per step = {M * 10e3 / 1e9:.1f} GB (larger than L2)"},
            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": B * 36, "d2h_bytes_per_step": 4,
                    "api": "Trainer.step(rays=pinned, gt=pinned, sync_loss=True): host-selected batch copied in, loss read back, every step"},
            "gpu_launches": timed_launches,

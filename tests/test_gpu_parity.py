@@ -12,6 +12,11 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16x3": 1e-4}        # BASELINE.json north_star tolerances (max abs err); bf16x3 = tensor-core fp32-class mode
 
 
+# all-five-outputs case, bf16: observed on B200 (round 2) 0.107 of the tensor max elementwise and 0.106 in relative L2
+# (worst tensor layers_0.0.weight); bounds are < 2x that.  fp32 / bf16x3 (gradients from the fp32 kernels): observed 9.6e-4.
+BF16_ALL5_MAX, BF16_ALL5_L2, FP32_ALL5_MAX = 0.2, 0.15, 3e-3
+
+
 def maxabs(a, b):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
     b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
@@ -233,20 +238,22 @@ def test_all_five_outputs_gradient(net, precision):
     cot = [g["cot_rgb"], g["cot_disp"], g["cot_alpha"], g["cot_acc"], g["cot_w"]]
     sum((a * torch.from_numpy(b).cuda()).sum() for a, b in zip(o5, cot)).backward()
     grads = {k[5:]: v for k, v in g.items() if k.startswith("grad.")}
+    worst = [0.0, 0.0]
     for k, p in net.named_parameters():
         if k in grads:
             scale = max(1e-6, float(np.abs(grads[k]).max()))
             # conditioning of this case is ~1.2e-2 even for fp32-vs-fp64 (see tests/test_oracle.py): random
-            # cotangents on alpha/weights cancel heavily over 12288 samples.  bf16 (8-bit mantissa
-            # activations and deltas) is held to 20% of the
-            # tensor's max elementwise and 15% in relative L2 norm (worst tensor: layers_0.0.weight, whose
-            # delta went through nine bf16 roundings; the well-conditioned train-step case is held to 5e-2).
+            # cotangents on alpha/weights cancel heavily over 12288 samples.  bf16 (8-bit mantissa activations and
+            # deltas): bounds = 2x the worst observed on B200 (BF16_ALL5_*), elementwise relative to the tensor's
+            # max and in relative L2 norm (worst tensor: layers_0.0.weight, whose delta went through nine roundings).
             err = maxabs(p.grad, grads[k])
+            l2 = float(np.linalg.norm(p.grad.cpu().numpy() - grads[k]) / max(1e-12, np.linalg.norm(grads[k])))
+            worst = [max(worst[0], err / scale), max(worst[1], l2)]
             if precision != "bf16":
-                assert err <= 3e-2 * scale, k
+                assert err <= FP32_ALL5_MAX * scale, k
             else:
-                l2 = float(np.linalg.norm(p.grad.cpu().numpy() - grads[k]) / max(1e-12, np.linalg.norm(grads[k])))
-                assert err <= 0.2 * scale and l2 <= 0.15, (k, err, scale, l2)
+                assert err <= BF16_ALL5_MAX * scale and l2 <= BF16_ALL5_L2, (k, err, scale, l2)
+    print(f"all-five-outputs gradient [{precision}]: worst elementwise err / tensor max {worst[0]:.3e}, worst relative L2 {worst[1]:.3e}")
 
 
 def test_full_size_properties(net, precision):
