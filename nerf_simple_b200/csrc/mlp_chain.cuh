@@ -836,38 +836,52 @@ struct DgradEpi {
 #endif
   }
 
-  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
-    const int bl = l + 1;
-    const int64_t T = p.num_tiles;
-    // ReLU mask (bit per element, loaded in prefetch): bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
-    const bool masked = bl >= 2;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const int col0 = c.half * 128 + q * 32;
-      const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
-      const uint32_t mw = q == 0 ? st.mask.x : (q == 1 ? st.mask.y : (q == 2 ? st.mask.z : st.mask.w));   // two 16-column steps
-      uint32_t a[32];
-      tmem_ld32(c.t_lane + col0, a);
-      tmem_ld_wait();
-      const float* ws = c.cf + kF32WSig + col0;
+  // 16 accumulator columns -> masked bf16 delta chunk pair in A[slot] (the next layer's A operand and wgrad's operand)
+  template <bool kMasked, bool kSigma>
+  __device__ static __forceinline__ void cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, uint32_t field, float gsig) {
+    const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
+    const float* ws = c.cf + kF32WSig + col0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x[8];
+    for (int j = 0; j < 2; ++j) {
+      float x[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          x[e] = __uint_as_float(a[8 * j + e]);
-          if (bl == 2) x[e] = fmaf(st.g.w, ws[8 * j + e], x[e]);  // + d_sigma * w_sigma (sigma head reads h7)
-        }
-        uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
-                 w3 = pack_bf16x2(x[6], x[7]);
-        if (masked) {
-          const uint32_t field = (mw >> (16 * (j >> 1))) & 0xFFFFu;
-          const int k0 = 4 * (j & 1);
-          w0 &= pair_mask_word(field, k0); w1 &= pair_mask_word(field, k0 + 1);
-          w2 &= pair_mask_word(field, k0 + 2); w3 &= pair_mask_word(field, k0 + 3);
-        }
-        st_shared_v4(c.a_img + sw_off(c, kb, j0 + j), w0, w1, w2, w3);
+      for (int e = 0; e < 8; ++e) {
+        x[e] = __uint_as_float(a[8 * j + e]);
+        if (kSigma) x[e] = fmaf(gsig, ws[8 * j + e], x[e]);  // + d_sigma * w_sigma (sigma head reads h7)
       }
+      uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
+               w3 = pack_bf16x2(x[6], x[7]);
+      if (kMasked) {
+        w0 &= pair_mask_word(field, 4 * j); w1 &= pair_mask_word(field, 4 * j + 1);
+        w2 &= pair_mask_word(field, 4 * j + 2); w3 &= pair_mask_word(field, 4 * j + 3);
+      }
+      st_shared_v4(c.a_img + sw_off(c, kb, j0 + j), w0, w1, w2, w3);
     }
+  }
+  // this thread's 128 columns in 16-column steps, the TMEM load of the next step in flight while the current one is
+  // converted (the single-buffered 32-column loads left the load latency exposed four times per layer)
+  template <bool kMasked, bool kSigma>
+  __device__ static __forceinline__ void layer_t(State& st, const TileCtx& c) {
+    const int cbase = c.half * 128;
+    uint32_t a0[16], a1[16];
+    tmem_ld16(c.t_lane + cbase, a0);
+#pragma unroll 1
+    for (int q = 0; q < 8; q += 2) {
+      const uint32_t mw = q == 0 ? st.mask.x : (q == 2 ? st.mask.y : (q == 4 ? st.mask.z : st.mask.w));   // two 16-column steps
+      tmem_ld_wait();
+      tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);
+      cols16<kMasked, kSigma>(c, a0, cbase + q * 16, mw & 0xFFFFu, st.g.w);
+      tmem_ld_wait();
+      if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
+      cols16<kMasked, kSigma>(c, a1, cbase + (q + 1) * 16, mw >> 16, st.g.w);
+    }
+  }
+
+  __device__ static void layer(const Params&, State& st, const TileCtx& c, int l) {
+    // ReLU mask (bit per element, loaded in prefetch): bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
+    const int bl = l + 1;
+    if (bl == 1) layer_t<false, false>(st, c);
+    else if (bl == 2) layer_t<true, true>(st, c);
+    else layer_t<true, false>(st, c);
   }
 };
