@@ -548,6 +548,7 @@ def bench_train(args, c, B, N, steps, warmup, loop_api=False):
                                     "api": "train.py:47-57 body unchanged: rg.select (device mode) -> train_imgs[ray_ids].cuda() -> render_nerf "
                                            "-> MSELoss -> backward -> torch.optim.Adam"}
         config.set_select("reference"); config.set_sampler("reference")
+    tr.close()
     del tr, rays_table, gt_table
     torch.cuda.empty_cache()
     return rec

@@ -207,6 +207,20 @@ __global__ void __launch_bounds__(256) adam_flat_state_kernel(float* __restrict_
   const float t = (float)(st->step + 1);
   const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
   const float step_size = st->lr / bc1;
+  const bool vec = i4 + 3 < n && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  if (vec) {   // the flat buffers of the Trainer: 16-byte aligned, padded to multiples of 4
+    float4 pp = *reinterpret_cast<float4*>(p + i4), mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * ga[k];
+      va[k] = beta2 * va[k] + (1.f - beta2) * ga[k] * ga[k];
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp; *reinterpret_cast<float4*>(m + i4) = mm; *reinterpret_cast<float4*>(v + i4) = vv;
+    return;
+  }
   for (int64_t i = i4; i < n && i < i4 + 4; ++i) {
     const float gi = g[i];
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;

@@ -96,13 +96,19 @@ class PeerBuffer:
         return (C.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
 
     def release(self):
+        """Collective: every rank unmaps the peers' buffers, then (after a barrier) frees its own.  Tensors made by
+        tensor() must not be used afterwards."""
+        import torch.distributed as dist
         lib = _lib.load()
-        for q in self._opened:
-            lib.nb200_p2p_close(C_void(q))
-        self._opened = []
-        if self.ptr:
-            lib.nb200_p2p_free(C_void(self.ptr))
-            self.ptr = None
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for q in self._opened:
+                lib.nb200_p2p_close(C_void(q))
+            self._opened = []
+            dist.barrier(group=self.group)
+            if self.ptr:
+                lib.nb200_p2p_free(C_void(self.ptr))
+                self.ptr = None
 
 
 def C_void(v):
@@ -318,6 +324,18 @@ class Trainer:
             with torch.cuda.graph(gb):
                 self._enqueue_step(part="update")
             self._graphs[select] = (ga, gb)
+
+    def close(self):
+        """Release the peer-shared gradient buffer (collective over the ranks; a no-op on one GPU).  The Trainer must
+        not be stepped afterwards."""
+        if self._p2p is not None:
+            buf = self._p2p[0]
+            self._graphs.clear()
+            for p in self.net.parameters():
+                p.grad = None
+            self.flat_grad = self.grads = None
+            self._p2p = None
+            buf.release()
 
     @property
     def launch_mode(self):

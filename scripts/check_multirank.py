@@ -88,5 +88,7 @@ dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     res["all_ranks_ok"] = bool(flags.min() > 0)
     print(json.dumps(res), flush=True)
+ok_all = bool(flags.min() > 0)
+tr.close()
 dist.destroy_process_group()
-sys.exit(0 if bool(flags.min() > 0) else 1)
+sys.exit(0 if ok_all else 1)
