@@ -399,7 +399,6 @@ def test_train_gradients_odd_tile_counts(net, golden_weights, B, N, rtol):
     ragged last tile): bf16 gradients against the ORACLE (numpy restatement of the reference's autograd) on the
     same inputs.  The bf16 deviation averages out with the number of samples (2.7e-2 at 4096 samples), hence the
     looser bound for 111 samples; an aliased or dropped tile would be off by O(1).  Absolute bound: north star."""
-    TOL_G = TOL
     from nerf_simple_b200 import config, ops, _lib
     g = load_golden("case_render_b1024_n64.npz")
     rays_np = g["rays"][:B]
