@@ -12,7 +12,7 @@ The same JSON line carries sub-records measured in the same run (`--workload all
   train          configs[2]: training step 4096 rays x 64 samples per GPU, fwd + bwd + Adam (data-parallel for N > 1)
   train_dp8192   configs[4]: 8192 rays per GPU, data-parallel, one all-reduce of the 595,844 gradients per step
   sharded_frame  configs[4]: ONE 1600x1600 frame split into ray bands over the ranks + one all_gather (strong scaling)
-  n128           the reference's default 128 samples/ray (configs/lego.yaml:6)
+  n128, train_n128   the reference's default 128 samples/ray (configs/lego.yaml:6), render and train step
 
 `--impl reference` times the UNMODIFIED reference (baseline/_ref, staged by scripts/stage_reference.sh; its own
 render_nerf, CPU, all host threads) on a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
@@ -486,7 +486,7 @@ def bench_train(args, c, B, N, steps, warmup, loop_api=False):
     M = B * N
     achieved = FLOP_TRAIN * M / (ms_step * 1e-3) / 1e12
     traffic, tsrc = load_traffic("train_step_mlp_kernels") if (B, N) == (4096, 64) else (None, None)
-    rec = {"metric": "rays/sec (64 samples/ray) train", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
+    rec = {"metric": f"rays/sec ({N} samples/ray) train", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": ms_step, "scaling": "weak", "dtype": args.precision, "samples_per_sec": value * N,
            "config": {"workload": f"training step {B} rays x {N} samples per GPU, L=10/4 posenc, fwd+bwd+Adam, fused compositing backward "
                                   f"(train.py:47-57)", "rays_table": "25 views 400x400 (4.0 M rays) on device",
@@ -602,6 +602,8 @@ def b200_arm(args, rank, local_rank, world):
         # sub-records of the same run (every rank takes part; rank 0 prints)
         line["train"] = bench_train(args, c, 4096, N, args.train_steps, 20, loop_api=True)
         line["train_dp8192"] = bench_train(args, c, 8192, N, max(100, args.train_steps // 2), 20)
+        if N != 128:   # the reference's own training shape: configs/lego.yaml batch_size 4096, Nf 128 (train.py:51)
+            line["train_n128"] = bench_train(args, c, 4096, 128, max(100, args.train_steps // 2), 20)
         line["sharded_frame"] = bench_sharded_frame(args, c, 1600, 1600, N, frames=max(3, args.steps // 4))
         r128 = bench_render(args, c, H, W, 128, max(3, args.steps // 4), 2, e2e=False, api=False)
         line["n128"] = {"value": r128["value"], "unit": "rays/s", "ms_per_step": r128["ms_per_step"], "samples_per_sec": r128["value"] * 128,
