@@ -6,7 +6,7 @@ the ray table and the ground-truth colours live on the device, a step is
     select -> Philox jitter -> fused MLP forward (saving bf16 tiles) -> compositing forward ->
     MSE gradient -> compositing backward -> delta chain -> wgrad -> [all-reduce] -> Adam
 and the 24 parameters / gradients are views of two flat fp32 buffers, so data-parallel training
-needs exactly one NCCL all-reduce of 595,844 floats per step.  Everything that varies
+needs exactly one all-reduce of 595,844 floats per step.  Everything that varies
 from step to step lives in a 32-byte device-resident state, so after two eager warm-up steps the
 whole step is captured in a CUDA graph and replayed (use_graph=True; with several ranks the gradient
 all-reduce is fused into the Adam kernel over NVLink peer memory, or -- NB200_P2P_ALLREDUCE=0 -- two
@@ -15,6 +15,7 @@ graphs are replayed around an eagerly launched NCCL all-reduce).  The batch can 
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import torch
@@ -53,7 +54,6 @@ class PeerBuffer:
     torch.distributed, and every rank opens the others' with its own device current."""
 
     def __init__(self, nbytes, device, group=None):
-        import ctypes as C
         import torch.distributed as dist
         lib = _lib.load()
         self.device, self.nbytes, self.group = device, int(nbytes), group
@@ -92,7 +92,6 @@ class PeerBuffer:
         return torch.as_tensor(_Iface(), device=self.device)
 
     def ptr_array(self, byte_offset=0):
-        import ctypes as C
         return (C.c_void_p * self.world)(*[p + byte_offset for p in self.ptrs])
 
     def release(self):
@@ -103,17 +102,12 @@ class PeerBuffer:
         torch.cuda.synchronize(self.device)
         with torch.cuda.device(self.device):
             for q in self._opened:
-                lib.nb200_p2p_close(C_void(q))
+                lib.nb200_p2p_close(C.c_void_p(q))
             self._opened = []
             dist.barrier(group=self.group)
             if self.ptr:
-                lib.nb200_p2p_free(C_void(self.ptr))
+                lib.nb200_p2p_free(C.c_void_p(self.ptr))
                 self.ptr = None
-
-
-def C_void(v):
-    import ctypes as C
-    return C.c_void_p(v)
 
 
 def allreduce_mean_(flat_grad, world_size, group=None):
