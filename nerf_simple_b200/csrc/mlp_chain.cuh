@@ -42,6 +42,7 @@ struct TileCtx {
   uint32_t r7s;      // (r & 7) << 4
   uint32_t a_img, e_img, t_lane;
   const float* cf;   // this launch's slot of the constant bank
+  const float* gf;   // the same fp32 tail in global memory (packed buffer)
 };
 __device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32_t j) {
   return kb * 16384u + c.rowoff + ((j << 4) ^ c.r7s);
@@ -49,6 +50,119 @@ __device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32
 
 __device__ __forceinline__ void slot_barrier(int slot) {  // the 256 epilogue threads of one slot
   asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory");
+}
+
+// ---------------------------------------------------------------- compile-time slab schedule
+// The MMA warp's issue loop is fully unrolled over (layer, slot, slab): A-operand offsets, instruction descriptors
+// and the accumulate flags are immediates, and the only runtime state is the ring position.  (Walking the
+// constant-bank SlabDesc table instead cost a chain of dependent indexed LDC + R2UR + LDCU per slab, ~700 cycles of
+// MMA-warp time for the 512 cycles of tensor work it issued: the issue warp, not the weights or the epilogue, was
+// the bottleneck of every chain kernel.)  The producer still walks the table (it is never late); check_schedules()
+// verifies on the host that table and compile-time schedule agree.
+#ifdef NB200_DEV
+constexpr bool kDevBuild = true;    // cycle counters of the MMA / epilogue / producer warps (NB200_DBG=8), never in the shipped library
+#else
+constexpr bool kDevBuild = false;
+#endif
+struct SlabC { int src, kb, n, ksteps, both_a; };
+constexpr int kSchedFwd = 0, kSchedBwd = 1, kSchedFwd3 = 2;
+__host__ __device__ constexpr int sched_fwd_slabs(int l) { return l == 0 ? 1 : ((l == 5 || l == 9) ? 5 : 4); }
+__host__ __device__ constexpr SlabC sched_fwd_slab(int l, int s) {
+  return l == 0 ? SlabC{1, 0, 256, 4, 0}
+                : (l == 9 ? (s < 4 ? SlabC{0, s, 128, 4, 0} : SlabC{1, 0, 128, 2, 0})
+                          : (s < 4 ? SlabC{0, s, 256, 4, 0} : SlabC{1, 0, 256, 4, 0}));
+}
+template <int kSched> __host__ __device__ constexpr int sched_slabs(int l) {
+  return kSched == kSchedFwd ? sched_fwd_slabs(l) : (kSched == kSchedBwd ? (l == 0 ? 2 : 4) : 2 * sched_fwd_slabs(l));
+}
+template <int kSched> __host__ __device__ constexpr SlabC sched_slab(int l, int s) {
+  if (kSched == kSchedFwd) return sched_fwd_slab(l, s);
+  if (kSched == kSchedBwd) return SlabC{0, s, 256, 4, 0};
+  SlabC c = sched_fwd_slab(l, s >> 1);   // bf16x3: every forward slab twice, hi (against A_hi and A_lo) then lo (A_hi only)
+  c.both_a = (s & 1) ? 0 : 1;
+  return c;
+}
+
+struct MmaRing { uint32_t stage, phase; };
+
+template <class Epi, int L, int SLOT, int S>
+__device__ __forceinline__ void issue_slab(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, bool replay,
+                                           bool release, MmaRing& r) {
+  constexpr SlabC sc = sched_slab<Epi::kSched>(L, S);
+  constexpr int NS = sched_slabs<Epi::kSched>(L);
+  if (!replay) {
+    mbar_wait(bar + kB_WFull + 8 * r.stage, r.phase, 400);
+    tc_fence_after();
+  }
+  constexpr uint32_t a_off = sc.src ? (kC_E + SLOT * kEBytes) : (kC_A + SLOT * kABytes + (uint32_t)sc.kb * 16384u);
+  const uint64_t adesc = desc_hi | (uint64_t)(((smem_base + a_off) >> 4) & 0x3FFFu);
+  const uint64_t bdesc = desc_hi | (uint64_t)(((smem_base + kC_W + r.stage * kCStageBytes) >> 4) & 0x3FFFu);
+  constexpr uint32_t idesc = umma_idesc_bf16(256, sc.n, 0, 0);
+  const uint32_t d_tmem = tmem_base + (uint32_t)SLOT * 256u;
+  if (elect_one()) {
+    umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, S == 0 ? 0u : 1u);   // +2 in the address field = +32 bytes
+    umma_bf16_2cta(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+    if (sc.ksteps > 2) {
+      umma_bf16_2cta(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+      umma_bf16_2cta(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+    }
+    if (sc.both_a) {   // bf16x3: the same B slab against the residual image A_lo (the other slot's buffer)
+      const uint64_t alo = adesc + ((sc.src ? kEBytes : kABytes) >> 4);
+      umma_bf16_2cta(d_tmem, alo, bdesc, idesc, 1u);
+      umma_bf16_2cta(d_tmem, alo + 2, bdesc + 2, idesc, 1u);
+      if (sc.ksteps > 2) {
+        umma_bf16_2cta(d_tmem, alo + 4, bdesc + 4, idesc, 1u);
+        umma_bf16_2cta(d_tmem, alo + 6, bdesc + 6, idesc, 1u);
+      }
+    }
+    if (release) umma_commit_2cta(bar + kB_WEmpty + 8 * r.stage);   // the last user frees the stage
+    if (S == NS - 1) umma_commit_2cta(bar + kB_Acc + 8 * SLOT);
+  }
+  __syncwarp();
+  if (++r.stage == kCStages) { r.stage = 0; r.phase ^= 1; }
+}
+template <class Epi, int L, int SLOT, int... S>
+__device__ __forceinline__ void issue_slabs(std::integer_sequence<int, S...>, uint32_t smem_base, uint32_t bar, uint32_t tmem_base,
+                                            uint64_t desc_hi, bool replay, bool release, MmaRing& r) {
+  (issue_slab<Epi, L, SLOT, S>(smem_base, bar, tmem_base, desc_hi, replay, release, r), ...);
+}
+// one layer of a pair of in-flight tiles: slot 0, then slot 1 against the slabs that are still resident
+template <class Epi, int L>
+__device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, int nslots,
+                                            MmaRing& r, uint32_t& act_parity0, uint32_t& act_parity1, long long& t_act) {
+  constexpr int NS = sched_slabs<Epi::kSched>(L);
+  using Seq = std::make_integer_sequence<int, NS>;
+  const bool shared = (nslots == 2 && NS <= kCStages);   // do both slots consume one copy of the layer's slabs?
+  const MmaRing r0 = r;
+#ifdef NB200_DEV
+  long long tw0 = clock64();
+#endif
+  mbar_wait(bar + kB_Act, act_parity0, 300 + L);
+  act_parity0 ^= 1;
+#ifdef NB200_DEV
+  t_act += clock64() - tw0;
+#endif
+  tc_fence_after();
+  issue_slabs<Epi, L, 0>(Seq{}, smem_base, bar, tmem_base, desc_hi, false, !shared, r);
+  if (Epi::kSlots == 2 && nslots == 2) {
+#ifdef NB200_DEV
+    tw0 = clock64();
+#endif
+    mbar_wait(bar + kB_Act + 8, act_parity1, 350 + L);
+    act_parity1 ^= 1;
+#ifdef NB200_DEV
+    t_act += clock64() - tw0;
+#endif
+    tc_fence_after();
+    if (shared) r = r0;   // replay the resident slabs
+    issue_slabs<Epi, L, Epi::kSlots == 2 ? 1 : 0>(Seq{}, smem_base, bar, tmem_base, desc_hi, shared, true, r);
+  }
+}
+template <class Epi, int... L>
+__device__ __forceinline__ void issue_layers(std::integer_sequence<int, L...>, uint32_t smem_base, uint32_t bar, uint32_t tmem_base,
+                                             uint64_t desc_hi, int nslots, MmaRing& r, uint32_t& act_parity0, uint32_t& act_parity1,
+                                             long long& t_act) {
+  (issue_layer<Epi, L>(smem_base, bar, tmem_base, desc_hi, nslots, r, act_parity0, act_parity1, t_act), ...);
 }
 
 template <class Epi>
@@ -102,10 +216,12 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     c.e_img = smem_base + kC_E + slot * kEBytes;
     c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
     c.cf = c_f32 + p.cslot * kF32Floats;
+    c.gf = reinterpret_cast<const float*>(p.packed + (Epi::kSched == kSchedFwd3 ? c_layout.f32_off3 : c_layout.f32_off));
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
     uint32_t acc_parity = 0, free_parity = 0;
     typename Epi::State st;
     bool first_step = true;
+    long long t_epi = 0, t_accw = 0, t_pro = 0;
     // hand a finished tile image to the MMA warp (leader's act barrier) and, in the training kernels, to this slot's
     // store warp; `to_mma` is false after the last layer of a tile
     auto publish = [&](bool to_mma) {
@@ -131,17 +247,38 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       // tiles last, so they are the ones still in L2 when the backward starts
       if (Epi::kReverseTiles) c.tile = 2 * (PT - 1 - (cid + k * C)) + rank;
       reclaim();
+      long long tq0 = 0;
+      if constexpr (Epi::kHasDbg && kDevBuild) tq0 = clock64();
       Epi::begin_tile(p, st, c);
       publish(true);
+      if constexpr (Epi::kHasDbg && kDevBuild) t_pro += clock64() - tq0;
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         Epi::prefetch(p, st, c, l);  // global loads that do not depend on the accumulator
+        if constexpr (Epi::kHasDbg && kDevBuild) tq0 = clock64();
         mbar_wait(bar + kB_Acc + 8 * slot, acc_parity, 100 + l);
         acc_parity ^= 1;
         tc_fence_after();
+        long long tq1 = 0;
+        if constexpr (Epi::kHasDbg && kDevBuild) { tq1 = clock64(); t_accw += tq1 - tq0; }
         reclaim();
         Epi::layer(p, st, c, l);
         if (Epi::kBulkStore || l + 1 < Epi::kNumLayers) publish(l + 1 < Epi::kNumLayers);
+        if constexpr (Epi::kHasDbg && kDevBuild) {
+          const long long tq2 = clock64();
+          t_epi += tq2 - tq1;
+          if ((p.dbg & 8) && threadIdx.x == 0 && rank == 0 && p.dbg_counters) {   // per-layer split (fire-and-forget reds)
+            atomicAdd(p.dbg_counters + 16 + l, (unsigned long long)(tq2 - tq1));
+            atomicAdd(p.dbg_counters + 32 + l, (unsigned long long)(tq1 - tq0));
+          }
+        }
         Epi::after_publish(p, c, l);
+      }
+    }
+    if constexpr (Epi::kHasDbg && kDevBuild) {
+      if ((p.dbg & 8) && threadIdx.x == 0 && rank == 0 && p.dbg_counters) {   // warp 0 of the leader CTA
+        atomicAdd(p.dbg_counters + 4, (unsigned long long)t_epi);
+        atomicAdd(p.dbg_counters + 5, (unsigned long long)t_accw);
+        atomicAdd(p.dbg_counters + 6, (unsigned long long)t_pro);
       }
     }
     if (Epi::kBulkStore && !first_step) mbar_wait(bar + kB_StoreFree + 8 * slot, free_parity, 501);   // last store read its image
@@ -149,6 +286,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // ==================================== weight producer ====================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long t_pempty = 0;
       for (int64_t pr = 0; pr * Epi::kSlots < my_pt; ++pr) {
         const int nslots = (Epi::kSlots == 2 && my_pt - 2 * pr >= 2) ? 2 : 1;
         int s0 = 0;
@@ -159,6 +297,12 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
           for (int rep = 0; rep < reps; ++rep) {
             for (int s = s0; s <= s1; ++s) {
               const uint32_t half = slabs[s].bytes >> 1;
+              if constexpr (Epi::kHasDbg && kDevBuild) {
+                const long long tp0 = clock64();
+                mbar_wait(bar + kB_WEmpty + 8 * stage, phase ^ 1, 200);
+                const long long tp1 = clock64();
+                t_pempty += tp1 - tp0;
+              } else
               mbar_wait(bar + kB_WEmpty + 8 * stage, phase ^ 1, 200);
               // both CTAs signal the LEADER's barrier: it expects the whole slab (two halves)
               if (rank == 0) mbar_arrive_expect_tx(bar + kB_WFull + 8 * stage, slabs[s].bytes);
@@ -170,6 +314,9 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
           }
           s0 = s1 + 1;
         }
+      }
+      if constexpr (Epi::kHasDbg && kDevBuild) {
+        if ((p.dbg & 8) && rank == 0 && p.dbg_counters) atomicAdd(p.dbg_counters + 7, (unsigned long long)t_pempty);
       }
     }
   } else if (warp >= kCStoreWarp0) {
@@ -198,78 +345,28 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // peer CTA: nothing to issue (its MMAs are issued by the leader, its TMA signals the leader)
   } else {
     // ================================ leader CTA: MMA issuer ================================
-    // The whole warp walks the schedule convergently (loop state and descriptors stay in uniform
-    // registers); one elected lane issues the tcgen05 instructions.
-    uint32_t stage = 0, phase = 0;
+    // The whole warp walks the (compile-time unrolled) schedule convergently; one elected lane issues the tcgen05
+    // instructions.
+    MmaRing ring{0u, 0u};
     uint32_t act_parity0 = 0, act_parity1 = 0;
-    long long t_act = 0, t_wfull = 0, t_wpeer = 0, t_begin = clock64();
+    long long t_act = 0;
+#ifdef NB200_DEV
+    const long long t_begin = clock64();
+#endif
     const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);  // LBO/SBO/version/swizzle bits
     for (int64_t pr = 0; pr * Epi::kSlots < my_pt; ++pr) {
       const int nslots = (Epi::kSlots == 2 && my_pt - 2 * pr >= 2) ? 2 : 1;
-      int s0 = 0;
-      for (int l = 0; l < Epi::kNumLayers; ++l) {
-        int s1 = s0;
-        while (!slabs[s1].last) ++s1;
-        const bool shared = (nslots == 2 && s1 - s0 + 1 <= kCStages);
-        const uint32_t stage0 = stage, phase0 = phase;
-        for (int slot = 0; slot < nslots; ++slot) {
-          long long tw0 = clock64();
-          if (slot == 0) { mbar_wait(bar + kB_Act, act_parity0, 300 + l); act_parity0 ^= 1; }
-          else { mbar_wait(bar + kB_Act + 8, act_parity1, 350 + l); act_parity1 ^= 1; }
-          t_act += clock64() - tw0;
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-          const bool replay = shared && slot == 1;  // slabs already resident from slot 0's pass
-          if (replay) { stage = stage0; phase = phase0; }
-          for (int s = s0; s <= s1; ++s) {
-            if (!replay) {
-              long long tw1 = clock64();
-              mbar_wait(bar + kB_WFull + 8 * stage, phase, 400);
-              t_wfull += clock64() - tw1;
-              tc_fence_after();
-            }
-            const uint32_t a_addr = slabs[s].src ? (smem_base + kC_E + slot * kEBytes)
-                                                 : (smem_base + kC_A + slot * kABytes + slabs[s].kb * 16384u);
-            const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
-            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_base + kC_W + stage * kCStageBytes) >> 4) & 0x3FFFu);
-            const uint32_t idesc = umma_idesc_bf16(256, slabs[s].n, 0, 0);
-            const uint32_t first = slabs[s].first ? 0u : 1u;
-            const int ksteps = slabs[s].ksteps;
-            const bool release = !(shared && slot == 0);  // the last user frees the stage
-            if (elect_one()) {
-              umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, first);   // +2 in the address field = +32 bytes
-              umma_bf16_2cta(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-              if (ksteps > 2) {
-                umma_bf16_2cta(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                umma_bf16_2cta(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-              }
-              if (Epi::kSplit3 && (slabs[s].flags & kSlabBothA)) {   // bf16x3: the same B slab against the residual image A_lo (the other slot's buffer)
-                const uint64_t alo = adesc + ((slabs[s].src ? kEBytes : kABytes) >> 4);
-                umma_bf16_2cta(d_tmem, alo, bdesc, idesc, 1u);
-                umma_bf16_2cta(d_tmem, alo + 2, bdesc + 2, idesc, 1u);
-                if (ksteps > 2) {
-                  umma_bf16_2cta(d_tmem, alo + 4, bdesc + 4, idesc, 1u);
-                  umma_bf16_2cta(d_tmem, alo + 6, bdesc + 6, idesc, 1u);
-                }
-              }
-              if (release) umma_commit_2cta(bar + kB_WEmpty + 8 * stage);
-              if (s == s1) umma_commit_2cta(bar + kB_Acc + 8 * slot);
-            }
-            __syncwarp();
-            if (++stage == kCStages) { stage = 0; phase ^= 1; }
-          }
-        }
-        s0 = s1 + 1;
-      }
+      issue_layers<Epi>(std::make_integer_sequence<int, Epi::kNumLayers>{}, smem_base, bar, tmem_base, desc_hi, nslots, ring,
+                        act_parity0, act_parity1, t_act);
     }
-    if constexpr (Epi::kHasDbg) {
+#ifdef NB200_DEV
+    if constexpr (Epi::kHasDbg && kDevBuild) {
       if ((p.dbg & 8) && lane == 0 && p.dbg_counters) {
         atomicAdd(p.dbg_counters + 0, (unsigned long long)t_act);
-        atomicAdd(p.dbg_counters + 1, (unsigned long long)t_wfull);
-        atomicAdd(p.dbg_counters + 2, (unsigned long long)t_wpeer);
         atomicAdd(p.dbg_counters + 3, (unsigned long long)(clock64() - t_begin));
       }
     }
+#endif
   }
   __syncwarp();
   tc_fence_before();
@@ -423,7 +520,14 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float x[8];
+#ifdef NB_PROBE_NOBIAS   // timing probe only (wrong results)
+    const float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+#elif defined(NB_BIAS_LDG)
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j)),
+                 b1 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j + 4));
+#else
     const float4 b0 = *reinterpret_cast<const float4*>(b + 8 * j), b1 = *reinterpret_cast<const float4*>(b + 8 * j + 4);
+#endif
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
     add_f32x2(x[0], x[1], b0.x, b0.y); add_f32x2(x[2], x[3], b0.z, b0.w);
@@ -441,7 +545,11 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
       w2 = pack_bf16x2(x[4], x[5]); w3 = pack_bf16x2(x[6], x[7]);
     }
     const uint32_t o = sw_off(c, kb, j0 + j);
+#ifdef NB_PROBE_NOSTS   // timing probe only (wrong results)
+    if (w0 == 0x12345678u && w1 == w2 && w3 == 0x9abcdef0u) st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+#else
     st_shared_v4(c.a_img + o, w0, w1, w2, w3);
+#endif
   }
 }
 
@@ -450,6 +558,9 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 // step in flight while the current one is converted (double buffer); ReLU is fused into the
 // fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), biases come from the constant bank and are
 // added two at a time (add.f32x2).
+#ifdef NB_PROBE_NOLDTM   // timing probe only (wrong results): no TMEM reads in the hidden-layer epilogue
+#define tmem_ld16(addr, arr) do { _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) arr[i_] = (addr) + (uint32_t)i_; } while (0)
+#endif
 template <bool kRelu, bool kSigma, bool kSave>
 __device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float& sigma) {
   const int cbase = c.half * 128;
@@ -465,6 +576,9 @@ __device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float
     epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, sigma);
   }
 }
+#ifdef NB_PROBE_NOLDTM
+#undef tmem_ld16
+#endif
 
 template <bool kSave, bool kRender = false>
 struct FwdEpi {
@@ -472,8 +586,8 @@ struct FwdEpi {
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
+  static constexpr int kSched = kSchedFwd;
   static constexpr int kSlots = 2;
-  static constexpr bool kSplit3 = false;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
   struct State {
@@ -660,8 +774,8 @@ struct FwdEpi3 {
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = false;
+  static constexpr int kSched = kSchedFwd3;
   static constexpr int kSlots = 1;
-  static constexpr bool kSplit3 = true;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
   struct State {
@@ -776,8 +890,8 @@ struct DgradEpi {
   using Params = BwdParams;
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = true;
+  static constexpr int kSched = kSchedBwd;
   static constexpr int kSlots = 2;
-  static constexpr bool kSplit3 = false;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   static constexpr bool kReverseTiles = true;
   struct State { float4 g; uint4 mask; };

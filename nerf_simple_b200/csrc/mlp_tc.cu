@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "stream_common.cuh"
@@ -155,8 +156,20 @@ static void build_layout() {
   h_layout.total_bytes3 = x.off + kF32Floats * (uint32_t)sizeof(float);
 }
 
+// The MMA warps walk a compile-time schedule (mlp_chain.cuh: sched_slab), the weight producers and the packer this
+// table: they must describe the same slabs in the same order.
+template <int kSched>
+static bool schedule_matches(const SlabDesc* tab, int num, int layers);
+static bool check_schedules();
+
 static void ensure_host_layout() {   // caller holds g_mu
-  if (!h_layout_built) { build_layout(); h_layout_built = true; }
+  if (h_layout_built) return;
+  build_layout();
+  if (!check_schedules()) {
+    fprintf(stderr, "nb200: packed-weight table and compile-time MMA schedule disagree\n");
+    abort();
+  }
+  h_layout_built = true;
 }
 static int ensure_layout() {
   int dev = 0;
@@ -283,6 +296,28 @@ __device__ __forceinline__ void encode_row(const float* x, uint32_t img_base, ui
 
 #include "mlp_tc_bwd.cuh"
 #include "mlp_chain.cuh"
+
+template <int kSched>
+static bool schedule_matches(const SlabDesc* tab, int num, int layers) {
+  int i = 0;
+  for (int l = 0; l < layers; ++l) {
+    const int ns = sched_slabs<kSched>(l);
+    for (int k = 0; k < ns; ++k, ++i) {
+      if (i >= num) return false;
+      const SlabC c = sched_slab<kSched>(l, k);
+      const SlabDesc& d = tab[i];
+      if (d.src != c.src || d.kb != c.kb || d.n != c.n || d.ksteps != c.ksteps || ((d.flags & kSlabBothA) != 0) != (c.both_a != 0) ||
+          (d.first != 0) != (k == 0) || (d.last != 0) != (k == ns - 1) || d.bytes != (uint32_t)c.n * 128u)
+        return false;
+    }
+  }
+  return i == num;
+}
+static bool check_schedules() {
+  return schedule_matches<kSchedFwd>(h_layout.fwd, h_layout.num_fwd, kNumMmaLayers) &&
+         schedule_matches<kSchedBwd>(h_layout.bwd, h_layout.num_bwd, 9) &&
+         schedule_matches<kSchedFwd3>(h_layout.fwd3, h_layout.num_fwd3, kNumMmaLayers);
+}
 
 // ------------------------------------------------------------------------------ host API
 size_t tc_packed_bytes(int x3) {
@@ -465,11 +500,15 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   { const char* e = getenv("NB200_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.dbg & 8) {
     static unsigned long long* ctr = nullptr;
-    if (!ctr) { cudaMalloc(&ctr, 64); }
-    unsigned long long h[4];
-    cudaMemcpy(h, ctr, 32, cudaMemcpyDeviceToHost);   // counters of the previous launch (debug only; syncs)
-    printf("nb200 dbg: mma-warp cycles wait_act=%llu wait_wfull=%llu wait_wpeer=%llu total=%llu\n", h[0], h[1], h[2], h[3]);
-    cudaMemset(ctr, 0, 64);
+    if (!ctr) { cudaMalloc(&ctr, 512); cudaMemset(ctr, 0, 512); }
+    unsigned long long h[64];
+    cudaMemcpy(h, ctr, 512, cudaMemcpyDeviceToHost);   // counters of the previous launch (debug only; syncs)
+    printf("nb200 dbg: mma-warp cycles wait_act=%llu total=%llu | epilogue warp 0: layers=%llu wait_acc=%llu prologue=%llu | producer wait_empty=%llu\n",
+           h[0], h[3], h[4], h[5], h[6], h[7]);
+    printf("nb200 dbg: epilogue warp 0 per layer, busy | wait_acc (share of total):");
+    for (int l = 0; l < 10; ++l) printf(" L%d %.1f|%.1f", l, 100.0 * (double)h[16 + l] / (double)(h[3] ? h[3] : 1), 100.0 * (double)h[32 + l] / (double)(h[3] ? h[3] : 1));
+    printf("\n");
+    cudaMemset(ctr, 0, 512);
     p.dbg_counters = ctr;
   }
 #endif
