@@ -23,7 +23,12 @@ constexpr uint32_t kC_A = 0, kC_E = 2 * kABytes, kC_W = kC_E + 2 * kEBytes;
 constexpr int kCStages = 4;
 constexpr uint32_t kCStageBytes = 16384;
 constexpr uint32_t kC_Bar = kC_W + kCStages * kCStageBytes;  // 229376
-constexpr uint32_t kCSmemLaunch = kC_Bar + 256 + 1024;
+// behind the barrier block: the biases of the layer whose epilogue comes next, one 1 KB fp32 row per slot (staged by the
+// slot's own 256 threads while they wait for the accumulator).  The epilogue reads them with warp-uniform LDS.128;
+// constant-bank loads in ANY form (indexed LDC.64, or LDCU.128 into uniform registers when the address is an
+// immediate) cost ~1,350 of the ~2,400 cycles a hidden-layer epilogue took.
+constexpr uint32_t kC_Bias = kC_Bar + 256;
+constexpr uint32_t kCSmemLaunch = kC_Bias + 2 * 1024;   // 231,680 of the 232,448 B a CTA can have: the base must be 1 KB aligned
 constexpr int kCThreads = 640;
 constexpr int kCProducerWarp = 16, kCMmaWarp = 17, kCStoreWarp0 = 18;
 // barrier offsets inside the barrier block
@@ -41,6 +46,7 @@ struct TileCtx {
   uint32_t rowoff;   // r * 128
   uint32_t r7s;      // (r & 7) << 4
   uint32_t a_img, e_img, t_lane;
+  uint32_t b_img;    // the slot's staged bias row (shared memory)
   const float* cf;   // this launch's slot of the constant bank
   const float* gf;   // the same fp32 tail in global memory (packed buffer)
 };
@@ -168,8 +174,12 @@ __device__ __forceinline__ void issue_layers(std::integer_sequence<int, L...>, u
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCThreads, 1)
 chain_kernel(const __grid_constant__ typename Epi::Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t chain_smem[];
+  const uint32_t smem_base = smem_u32(chain_smem);
+  if (smem_base & 1023u) {   // the SWIZZLE_128B images need it, and there is no slack left to round up
+    if (threadIdx.x == 0) printf("nb200: dynamic shared memory base 0x%x is not 1 KB aligned\n", smem_base);
+    __trap();
+  }
   const uint32_t bar = smem_base + kC_Bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -215,7 +225,12 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     c.a_img = smem_base + kC_A + slot * kABytes;
     c.e_img = smem_base + kC_E + slot * kEBytes;
     c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
+    c.b_img = smem_base + kC_Bias + (uint32_t)slot * 1024u;
+#ifdef NB_PROBE_SLOT0
+    c.cf = c_f32;
+#else
     c.cf = c_f32 + p.cslot * kF32Floats;
+#endif
     c.gf = reinterpret_cast<const float*>(p.packed + (Epi::kSched == kSchedFwd3 ? c_layout.f32_off3 : c_layout.f32_off));
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
     uint32_t acc_parity = 0, free_parity = 0;
@@ -232,6 +247,16 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         if (Epi::kBulkStore) mbar_arrive(bar + kB_Written + 8 * slot);
         if (to_mma) mbar_arrive_cluster(act_remote);
       }
+    };
+    // the biases of layer l -> the slot's staging row: one constant load + store per thread, between two barriers of
+    // the slot's 256 threads (everybody has finished with the previous row / the new row is visible).  Called right
+    // after a publish, i.e. while the slot would wait for its next accumulator anyway.
+    auto stage_bias = [&](int l) {
+      if (!Epi::kStageBias) return;
+      slot_barrier(slot);
+      const uint32_t t = threadIdx.x & 255u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + t * 4u), "f"(c.cf[kF32Bias + l * 256 + (int)t]) : "memory");
+      slot_barrier(slot);
     };
     // before overwriting A[slot] / E[slot]: the bulk store of the previous image must have read it
     auto reclaim = [&]() {
@@ -251,6 +276,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       if constexpr (Epi::kHasDbg && kDevBuild) tq0 = clock64();
       Epi::begin_tile(p, st, c);
       publish(true);
+      stage_bias(0);
       if constexpr (Epi::kHasDbg && kDevBuild) t_pro += clock64() - tq0;
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         Epi::prefetch(p, st, c, l);  // global loads that do not depend on the accumulator
@@ -271,6 +297,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
             atomicAdd(p.dbg_counters + 32 + l, (unsigned long long)(tq1 - tq0));
           }
         }
+        if (l + 1 < Epi::kNumLayers) stage_bias(l + 1);
         Epi::after_publish(p, c, l);
       }
     }
@@ -514,7 +541,6 @@ __device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint
 // (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
 template <bool kRelu, bool kSigma, bool kSave>
 __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, float& sigma) {
-  const float* b = c.cf + bias_off + col0;
   const float* ws = c.cf + kF32WSig + col0;
   const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
 #pragma unroll
@@ -522,16 +548,26 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
     float x[8];
 #ifdef NB_PROBE_NOBIAS   // timing probe only (wrong results)
     const float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+#elif defined(NB_PROBE_LDSBIAS)   // timing probe only (wrong results): "biases" read from shared memory at a warp-uniform address
+    float4 b0, b1;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(c.e_img + (uint32_t)(col0 + 8 * j) * 4u));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(c.e_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
 #elif defined(NB_BIAS_LDG)
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j)),
                  b1 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j + 4));
 #else
-    const float4 b0 = *reinterpret_cast<const float4*>(b + 8 * j), b1 = *reinterpret_cast<const float4*>(b + 8 * j + 4);
+    float4 b0, b1;   // staged row of this layer, warp-uniform address (broadcast)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(c.b_img + (uint32_t)(col0 + 8 * j) * 4u));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(c.b_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
 #endif
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
+#ifdef NB_SCALAR_BIAS
+    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+#else
     add_f32x2(x[0], x[1], b0.x, b0.y); add_f32x2(x[2], x[3], b0.z, b0.w);
     add_f32x2(x[4], x[5], b1.x, b1.y); add_f32x2(x[6], x[7], b1.z, b1.w);
+#endif
     if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
 #pragma unroll
       for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[8 * j + e], sigma);
@@ -561,12 +597,12 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 #ifdef NB_PROBE_NOLDTM   // timing probe only (wrong results): no TMEM reads in the hidden-layer epilogue
 #define tmem_ld16(addr, arr) do { _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) arr[i_] = (addr) + (uint32_t)i_; } while (0)
 #endif
-template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float& sigma) {
-  const int cbase = c.half * 128;
+template <bool kRelu, bool kSigma, bool kSave, int kHalf>
+__device__ __forceinline__ void epi_hidden_h(const TileCtx& c, int bias_off, float& sigma) {
+  constexpr int cbase = kHalf * 128;
   uint32_t a0[16], a1[16];
   tmem_ld16(c.t_lane + cbase, a0);
-#pragma unroll 1
+#pragma unroll
   for (int q = 0; q < 8; q += 2) {
     tmem_ld_wait();                                       // a0 (step q) has landed
     tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);       // step q+1 in flight
@@ -575,6 +611,15 @@ __device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float
     if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
     epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, sigma);
   }
+}
+// The column half is dispatched to a compile-time constant: the bias (and sigma-head weight) addresses are then
+// "uniform base + immediate", which ptxas serves through the uniform datapath (LDCU) instead of per-thread indexed
+// LDC.  The indexed loads, 8 per 16 columns, saturated the MIO/ADU path: 31 % of all warp stall samples of the
+// forward kernel sat on them (stall_mio), and removing the bias path altogether was worth 16 % of the frame time.
+template <bool kRelu, bool kSigma, bool kSave>
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float& sigma) {
+  if (c.half == 0) epi_hidden_h<kRelu, kSigma, kSave, 0>(c, bias_off, sigma);
+  else epi_hidden_h<kRelu, kSigma, kSave, 1>(c, bias_off, sigma);
 }
 #ifdef NB_PROBE_NOLDTM
 #undef tmem_ld16
@@ -587,6 +632,7 @@ struct FwdEpi {
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
   static constexpr int kSched = kSchedFwd;
+  static constexpr bool kStageBias = true;
   static constexpr int kSlots = 2;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
@@ -681,14 +727,15 @@ struct FwdEpi {
         uint32_t a[32];
         tmem_ld32(c.t_lane + col0, a);
         tmem_ld_wait();
-        const float* b = c.cf + kF32Bias + 9 * 256 + col0;
         const float* w = c.cf + kF32WC1 + col0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float x[8];
+          float x[8], b[8];
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(c.b_img + (uint32_t)(col0 + 8 * j) * 4u));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(c.b_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            x[e] = fmaxf(__uint_as_float(a[8 * j + e]) + b[8 * j + e], 0.f);
+            x[e] = fmaxf(__uint_as_float(a[8 * j + e]) + b[e], 0.f);
             rgb[0] = fmaf(x[e], w[8 * j + e], rgb[0]);
             rgb[1] = fmaf(x[e], w[128 + 8 * j + e], rgb[1]);
             rgb[2] = fmaf(x[e], w[256 + 8 * j + e], rgb[2]);
@@ -775,6 +822,7 @@ struct FwdEpi3 {
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = false;
   static constexpr int kSched = kSchedFwd3;
+  static constexpr bool kStageBias = false;
   static constexpr int kSlots = 1;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
@@ -891,6 +939,7 @@ struct DgradEpi {
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = true;
   static constexpr int kSched = kSchedBwd;
+  static constexpr bool kStageBias = false;
   static constexpr int kSlots = 2;
   static constexpr int kNumLayers = 9;  // bl = 1..9
   static constexpr bool kReverseTiles = true;
