@@ -255,7 +255,9 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       if (!Epi::kStageBias) return;
       slot_barrier(slot);
       const uint32_t t = threadIdx.x & 255u;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + t * 4u), "f"(c.cf[kF32Bias + l * 256 + (int)t]) : "memory");
+      // from the packed buffer's fp32 tail in global memory (coalesced, L2-resident): 256 DIFFERENT constant-bank
+      // addresses per slot serialise in the constant cache (~1,000 cycles per staged row)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + t * 4u), "f"(__ldg(c.gf + kF32Bias + l * 256 + (int)t)) : "memory");
       slot_barrier(slot);
     };
     // before overwriting A[slot] / E[slot]: the bulk store of the previous image must have read it
@@ -298,7 +300,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
           }
         }
         if (l + 1 < Epi::kNumLayers) stage_bias(l + 1);
-        Epi::after_publish(p, c, l);
+        Epi::after_publish(p, st, c, l);
       }
     }
     if constexpr (Epi::kHasDbg && kDevBuild) {
@@ -536,29 +538,34 @@ __device__ __forceinline__ void composite_staged_ray(const FwdEpiParams& p, uint
   }
 }
 
+// Head weights in shared memory.  While E[slot] carries posd (K = 32: logical chunks 0..3 of every 128-byte row), the
+// other 64 bytes of each row are free; the forward kernels keep w_sigma, color_fc.2's weight and the two head biases
+// there (644 floats, written next to the posd encoding, once per tile), because the constant-bank loads of the head
+// weights made the sigma-head layer 2.7x and the colour layer 2.5x as long as a plain hidden layer.
+// Table float i lives in logical chunk 4 + (i/4)%4 of row i/16 (SWIZZLE_128B image, like everything else in E).
+constexpr uint32_t kTabWSig = 0, kTabWC1 = 256, kTabBC1 = 640, kTabBSig = 643, kTabFloats = 644;
+__host__ __device__ constexpr uint32_t tab_off(uint32_t i) {
+  return (i >> 4) * 128u + (((4u + ((i >> 2) & 3u)) ^ ((i >> 4) & 7u)) << 4) + (i & 3u) * 4u;
+}
+__device__ __forceinline__ float4 tab_ld4(uint32_t e_img, uint32_t i) {   // i % 4 == 0, warp-uniform
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(e_img + tab_off(i)));
+  return v;
+}
+
 // One hidden layer: accumulator (TMEM) + bias -> [ReLU] -> bf16 A operand of the next layer.  Each
 // thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
 // (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, int bias_off, float& sigma) {
-  const float* ws = c.cf + kF32WSig + col0;
+__device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, const float4 (&bq)[4], float& sigma) {
   const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     float x[8];
 #ifdef NB_PROBE_NOBIAS   // timing probe only (wrong results)
     const float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-#elif defined(NB_PROBE_LDSBIAS)   // timing probe only (wrong results): "biases" read from shared memory at a warp-uniform address
-    float4 b0, b1;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(c.e_img + (uint32_t)(col0 + 8 * j) * 4u));
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(c.e_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
-#elif defined(NB_BIAS_LDG)
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j)),
-                 b1 = __ldg(reinterpret_cast<const float4*>(c.gf + bias_off + col0 + 8 * j + 4));
 #else
-    float4 b0, b1;   // staged row of this layer, warp-uniform address (broadcast)
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(c.b_img + (uint32_t)(col0 + 8 * j) * 4u));
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(c.b_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
+    const float4 b0 = bq[2 * j], b1 = bq[2 * j + 1];
 #endif
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
@@ -569,8 +576,10 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
     add_f32x2(x[4], x[5], b1.x, b1.y); add_f32x2(x[6], x[7], b1.z, b1.w);
 #endif
     if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
+      const float4 s0 = tab_ld4(c.e_img, kTabWSig + (uint32_t)(col0 + 8 * j)), s1 = tab_ld4(c.e_img, kTabWSig + (uint32_t)(col0 + 8 * j + 4));
+      const float ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[8 * j + e], sigma);
+      for (int e = 0; e < 8; ++e) sigma = fmaf(fmaxf(x[e], 0.f), ws[e], sigma);
     }
     uint32_t w0, w1, w2, w3;
     if (kRelu) {
@@ -597,19 +606,29 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 #ifdef NB_PROBE_NOLDTM   // timing probe only (wrong results): no TMEM reads in the hidden-layer epilogue
 #define tmem_ld16(addr, arr) do { _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) arr[i_] = (addr) + (uint32_t)i_; } while (0)
 #endif
+// the 16 staged biases of columns [col0, col0 + 16): warp-uniform LDS.128 (broadcast), issued BEFORE the wait for the
+// TMEM load they are added to, so that their latency hides behind it
+__device__ __forceinline__ void load_bias16(const TileCtx& c, int col0, float4 (&bq)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq[i].x), "=f"(bq[i].y), "=f"(bq[i].z), "=f"(bq[i].w) : "r"(c.b_img + (uint32_t)(col0 + 4 * i) * 4u));
+}
 template <bool kRelu, bool kSigma, bool kSave, int kHalf>
-__device__ __forceinline__ void epi_hidden_h(const TileCtx& c, int bias_off, float& sigma) {
+__device__ __forceinline__ void epi_hidden_h(const TileCtx& c, float& sigma) {
   constexpr int cbase = kHalf * 128;
   uint32_t a0[16], a1[16];
+  float4 bq[4];
   tmem_ld16(c.t_lane + cbase, a0);
 #pragma unroll
   for (int q = 0; q < 8; q += 2) {
+    load_bias16(c, cbase + q * 16, bq);
     tmem_ld_wait();                                       // a0 (step q) has landed
     tmem_ld16(c.t_lane + cbase + (q + 1) * 16, a1);       // step q+1 in flight
-    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bias_off, sigma);
+    epi_cols16<kRelu, kSigma, kSave>(c, a0, cbase + q * 16, bq, sigma);
+    load_bias16(c, cbase + (q + 1) * 16, bq);
     tmem_ld_wait();                                       // a1 has landed
     if (q + 2 < 8) tmem_ld16(c.t_lane + cbase + (q + 2) * 16, a0);
-    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bias_off, sigma);
+    epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bq, sigma);
   }
 }
 // The column half is dispatched to a compile-time constant: the bias (and sigma-head weight) addresses are then
@@ -617,9 +636,9 @@ __device__ __forceinline__ void epi_hidden_h(const TileCtx& c, int bias_off, flo
 // LDC.  The indexed loads, 8 per 16 columns, saturated the MIO/ADU path: 31 % of all warp stall samples of the
 // forward kernel sat on them (stall_mio), and removing the bias path altogether was worth 16 % of the frame time.
 template <bool kRelu, bool kSigma, bool kSave>
-__device__ __forceinline__ void epi_hidden(const TileCtx& c, int bias_off, float& sigma) {
-  if (c.half == 0) epi_hidden_h<kRelu, kSigma, kSave, 0>(c, bias_off, sigma);
-  else epi_hidden_h<kRelu, kSigma, kSave, 1>(c, bias_off, sigma);
+__device__ __forceinline__ void epi_hidden(const TileCtx& c, float& sigma) {
+  if (c.half == 0) epi_hidden_h<kRelu, kSigma, kSave, 0>(c, sigma);
+  else epi_hidden_h<kRelu, kSigma, kSave, 1>(c, sigma);
 }
 #ifdef NB_PROBE_NOLDTM
 #undef tmem_ld16
@@ -651,7 +670,21 @@ struct FwdEpi {
   // image was handed to the MMA warp and the store warp, from the bf16 image in shared memory: the epilogue warps of
   // this slot would otherwise idle until their next accumulator is ready, so the ~130 extra instructions per thread
   // and layer stay off the critical path (inside the epilogue they cost the kernel 11 %).
-  __device__ static void after_publish(const Params& p, const TileCtx& c, int ml) {
+  __device__ static void after_publish(const Params& p, State& st, const TileCtx& c, int ml) {
+    if (ml == 5) {
+      // posx has been consumed by the skip layer's MMAs: the encoding buffer now carries posd (27 -> 64) for color_fc.0,
+      // plus the head-weight table in the free half of its rows.  Done here, behind the hand-off of h5, so that it
+      // runs while the slot waits for its next accumulator (inside the epilogue it cost ~2,300 cycles of the chain).
+      // (only logical chunks 0..3 = K 0..31 are written and read: chunks 4..7 of the rows belong to the table)
+      if (c.half == 0) encode_row<kLd, 0, 2>(st.v + 3, c.e_img, c.r, nullptr);
+      else encode_row<kLd, 2, 4>(st.v + 3, c.e_img, c.r, nullptr);
+#pragma unroll
+      for (uint32_t i = threadIdx.x & 255u; i < kTabFloats; i += 256u) {
+        const float v = __ldg(c.gf + (i < kTabWC1 ? kF32WSig + (int)i
+                                                  : (i < kTabBC1 ? kF32WC1 + (int)(i - kTabWC1) : (i < kTabBSig ? kF32BC1 + (int)(i - kTabBC1) : kF32BSig))));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.e_img + tab_off(i)), "f"(v) : "memory");
+      }
+    }
     if (!kSave || ml < 0 || ml == 8) return;
     const int64_t T = p.num_tiles;
     if (ml < 8) {
@@ -703,20 +736,14 @@ struct FwdEpi {
     if (ml == -1) tma_bulk_s2g(p.saved + saved_tensor_off(10, T) + (size_t)c.tile * 16384, c.e_img, 16384);        // posx
     else if (ml < 9) tma_bulk_s2g(p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536, c.a_img, 65536);    // h0..h7, g
     else tma_bulk_s2g(p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768, c.a_img, 32768);                  // c1
-    if (ml == 5) tma_bulk_s2g(p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384, c.e_img, 16384);         // posd
+    if (ml == 6) tma_bulk_s2g(p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384, c.e_img, 16384);         // posd (encoded behind h5's hand-off)
   }
 
   __device__ static void layer(const Params& p, State& st, const TileCtx& c, int ml) {
-    const int64_t T = p.num_tiles;
-    if (ml == 5) {
-      // posx has been consumed by the skip layer: the encoding buffer now carries posd (27 -> 64)
-      if (c.half == 0) encode_row<kLd, 0, 4>(st.v + 3, c.e_img, c.r, nullptr);
-      else encode_row<kLd, 4, 8>(st.v + 3, c.e_img, c.r, nullptr);
-    }
     if (ml < 9) {
-      if (ml == 7) epi_hidden<true, true, kSave>(c, kF32Bias + ml * 256, st.sigma);
-      else if (ml == 8) epi_hidden<false, false, kSave>(c, kF32Bias + ml * 256, st.sigma);  // layers_2: no act.
-      else epi_hidden<true, false, kSave>(c, kF32Bias + ml * 256, st.sigma);
+      if (ml == 7) epi_hidden<true, true, kSave>(c, st.sigma);
+      else if (ml == 8) epi_hidden<false, false, kSave>(c, st.sigma);  // layers_2: no act.
+      else epi_hidden<true, false, kSave>(c, st.sigma);
     } else {
       // color_fc.0 epilogue (128 columns, ReLU; this thread's half = 64 of them) + color_fc.2
       // (128 -> 3) on CUDA cores; the two halves of a row meet through the (now free) E buffer
@@ -727,18 +754,18 @@ struct FwdEpi {
         uint32_t a[32];
         tmem_ld32(c.t_lane + col0, a);
         tmem_ld_wait();
-        const float* w = c.cf + kF32WC1 + col0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x[8], b[8];
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(c.b_img + (uint32_t)(col0 + 8 * j) * 4u));
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(c.b_img + (uint32_t)(col0 + 8 * j + 4) * 4u));
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            x[e] = fmaxf(__uint_as_float(a[8 * j + e]) + b[e], 0.f);
-            rgb[0] = fmaf(x[e], w[8 * j + e], rgb[0]);
-            rgb[1] = fmaf(x[e], w[128 + 8 * j + e], rgb[1]);
-            rgb[2] = fmaf(x[e], w[256 + 8 * j + e], rgb[2]);
+          for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(a[8 * j + e]) + b[e], 0.f);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {   // color_fc.2 (128 -> 3), weights from the table in E[slot]
+            const float4 w0 = tab_ld4(c.e_img, kTabWC1 + (uint32_t)(k * 128 + col0 + 8 * j)), w1 = tab_ld4(c.e_img, kTabWC1 + (uint32_t)(k * 128 + col0 + 8 * j + 4));
+            rgb[k] = fmaf(x[0], w0.x, rgb[k]); rgb[k] = fmaf(x[1], w0.y, rgb[k]); rgb[k] = fmaf(x[2], w0.z, rgb[k]); rgb[k] = fmaf(x[3], w0.w, rgb[k]);
+            rgb[k] = fmaf(x[4], w1.x, rgb[k]); rgb[k] = fmaf(x[5], w1.y, rgb[k]); rgb[k] = fmaf(x[6], w1.z, rgb[k]); rgb[k] = fmaf(x[7], w1.w, rgb[k]);
           }
           if (kSave) {  // c1 tile image -> A[slot] K-blocks 0,1 (free after color_fc.0's MMAs), bulk-stored by store_tile
             const uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
@@ -753,8 +780,8 @@ struct FwdEpi {
       if (c.half == 0) {
         float4 o;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xaddr));
-        const float4 res = make_float4(rgb[0] + o.x + c.cf[kF32BC1], rgb[1] + o.y + c.cf[kF32BC1 + 1], rgb[2] + o.z + c.cf[kF32BC1 + 2],
-                                       st.sigma + o.w + c.cf[kF32BSig]);  // (r,g,b,sigma), utils/nets.py:43
+        const float4 hb = tab_ld4(c.e_img, kTabBC1);   // color_fc.2's bias, sigma_fc's bias
+        const float4 res = make_float4(rgb[0] + o.x + hb.x, rgb[1] + o.y + hb.y, rgb[2] + o.z + hb.z, st.sigma + o.w + hb.w);  // (r,g,b,sigma), utils/nets.py:43
         if (kRender) {
           // stage the row for the compositing warps in A[slot]: its last reader (color_fc.0's MMAs) is done and
           // the next writer (layer 0's epilogue of the next tile) runs only after every warp of the slot has
@@ -834,7 +861,7 @@ struct FwdEpi3 {
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd3; }
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
-  __device__ static void after_publish(const Params&, const TileCtx&, int) {}
+  __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
   __device__ static void store_tile(const Params&, const TileCtx&, int) {}
 
   __device__ static void encode(const float* x, const TileCtx& c, bool dirs) {
@@ -945,7 +972,7 @@ struct DgradEpi {
   static constexpr bool kReverseTiles = true;
   struct State { float4 g; uint4 mask; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
-  __device__ static void after_publish(const Params&, const TileCtx&, int) {}
+  __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
 
   // The ReLU mask of layer l is this thread's 16-byte row of the bit-mask tensor the forward pass wrote (one bit per
   // element instead of the 64 KB bf16 activation tile): ONE load per thread and layer, issued before the accumulator
