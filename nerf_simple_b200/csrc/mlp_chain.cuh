@@ -91,20 +91,27 @@ template <int kSched> __host__ __device__ constexpr SlabC sched_slab(int l, int 
 
 struct MmaRing { uint32_t stage, phase; };
 
-template <class Epi, int L, int SLOT, int S>
-__device__ __forceinline__ void issue_slab(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, bool replay,
-                                           bool release, MmaRing& r) {
+// Layers with the same slab list share one unrolled copy of the issue code (kept small: the fully unrolled version,
+// one copy per layer and slot, was 100 KB of instructions and thrashed the instruction cache of the training kernels).
+// Class representatives: forward 0 | 1 (all plain 256x256 layers) | 5 (skip) | 9 (color_fc.0); delta chain 0 | 1.
+template <int kSched> __host__ __device__ constexpr int sched_class_rep(int l) {
+  return kSched == kSchedBwd ? (l == 0 ? 0 : 1) : ((l == 0 || l == 5 || l == 9) ? l : 1);
+}
+
+template <class Epi, int L, int S>
+__device__ __forceinline__ void issue_slab(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, uint32_t slot,
+                                           bool replay, bool release, MmaRing& r) {
   constexpr SlabC sc = sched_slab<Epi::kSched>(L, S);
   constexpr int NS = sched_slabs<Epi::kSched>(L);
   if (!replay) {
     mbar_wait(bar + kB_WFull + 8 * r.stage, r.phase, 400);
     tc_fence_after();
   }
-  constexpr uint32_t a_off = sc.src ? (kC_E + SLOT * kEBytes) : (kC_A + SLOT * kABytes + (uint32_t)sc.kb * 16384u);
-  const uint64_t adesc = desc_hi | (uint64_t)(((smem_base + a_off) >> 4) & 0x3FFFu);
+  const uint32_t a_addr = smem_base + (sc.src ? kC_E + slot * kEBytes : kC_A + slot * kABytes + (uint32_t)sc.kb * 16384u);
+  const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
   const uint64_t bdesc = desc_hi | (uint64_t)(((smem_base + kC_W + r.stage * kCStageBytes) >> 4) & 0x3FFFu);
   constexpr uint32_t idesc = umma_idesc_bf16(256, sc.n, 0, 0);
-  const uint32_t d_tmem = tmem_base + (uint32_t)SLOT * 256u;
+  const uint32_t d_tmem = tmem_base + slot * 256u;
   if (elect_one()) {
     umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, S == 0 ? 0u : 1u);   // +2 in the address field = +32 bytes
     umma_bf16_2cta(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
@@ -122,53 +129,39 @@ __device__ __forceinline__ void issue_slab(uint32_t smem_base, uint32_t bar, uin
       }
     }
     if (release) umma_commit_2cta(bar + kB_WEmpty + 8 * r.stage);   // the last user frees the stage
-    if (S == NS - 1) umma_commit_2cta(bar + kB_Acc + 8 * SLOT);
+    if (S == NS - 1) umma_commit_2cta(bar + kB_Acc + 8 * slot);
   }
   __syncwarp();
   if (++r.stage == kCStages) { r.stage = 0; r.phase ^= 1; }
 }
-template <class Epi, int L, int SLOT, int... S>
+template <class Epi, int L, int... S>
 __device__ __forceinline__ void issue_slabs(std::integer_sequence<int, S...>, uint32_t smem_base, uint32_t bar, uint32_t tmem_base,
-                                            uint64_t desc_hi, bool replay, bool release, MmaRing& r) {
-  (issue_slab<Epi, L, SLOT, S>(smem_base, bar, tmem_base, desc_hi, replay, release, r), ...);
+                                            uint64_t desc_hi, uint32_t slot, bool replay, bool release, MmaRing& r) {
+  (issue_slab<Epi, L, S>(smem_base, bar, tmem_base, desc_hi, slot, replay, release, r), ...);
 }
-// one layer of a pair of in-flight tiles: slot 0, then slot 1 against the slabs that are still resident
+// one layer (of class representative L) for the in-flight tiles: slot 0, then slot 1 against the slabs that are still resident
 template <class Epi, int L>
-__device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, int nslots,
-                                            MmaRing& r, uint32_t& act_parity0, uint32_t& act_parity1, long long& t_act) {
+__device__ __forceinline__ void issue_layer(uint32_t smem_base, uint32_t bar, uint32_t tmem_base, uint64_t desc_hi, int nslots, int l,
+                                            MmaRing& r, uint32_t (&act_parity)[2], long long& t_act) {
   constexpr int NS = sched_slabs<Epi::kSched>(L);
   using Seq = std::make_integer_sequence<int, NS>;
   const bool shared = (nslots == 2 && NS <= kCStages);   // do both slots consume one copy of the layer's slabs?
   const MmaRing r0 = r;
+#pragma unroll 1
+  for (int slot = 0; slot < nslots; ++slot) {
 #ifdef NB200_DEV
-  long long tw0 = clock64();
+    const long long tw0 = clock64();
 #endif
-  mbar_wait(bar + kB_Act, act_parity0, 300 + L);
-  act_parity0 ^= 1;
-#ifdef NB200_DEV
-  t_act += clock64() - tw0;
-#endif
-  tc_fence_after();
-  issue_slabs<Epi, L, 0>(Seq{}, smem_base, bar, tmem_base, desc_hi, false, !shared, r);
-  if (Epi::kSlots == 2 && nslots == 2) {
-#ifdef NB200_DEV
-    tw0 = clock64();
-#endif
-    mbar_wait(bar + kB_Act + 8, act_parity1, 350 + L);
-    act_parity1 ^= 1;
+    if (slot == 0) { mbar_wait(bar + kB_Act, act_parity[0], 300 + l); act_parity[0] ^= 1; }
+    else { mbar_wait(bar + kB_Act + 8, act_parity[1], 350 + l); act_parity[1] ^= 1; }
 #ifdef NB200_DEV
     t_act += clock64() - tw0;
 #endif
     tc_fence_after();
-    if (shared) r = r0;   // replay the resident slabs
-    issue_slabs<Epi, L, Epi::kSlots == 2 ? 1 : 0>(Seq{}, smem_base, bar, tmem_base, desc_hi, shared, true, r);
+    const bool replay = shared && slot == 1;   // the slabs are already resident from slot 0's pass
+    if (replay) r = r0;
+    issue_slabs<Epi, L>(Seq{}, smem_base, bar, tmem_base, desc_hi, (uint32_t)slot, replay, !(shared && slot == 0), r);
   }
-}
-template <class Epi, int... L>
-__device__ __forceinline__ void issue_layers(std::integer_sequence<int, L...>, uint32_t smem_base, uint32_t bar, uint32_t tmem_base,
-                                             uint64_t desc_hi, int nslots, MmaRing& r, uint32_t& act_parity0, uint32_t& act_parity1,
-                                             long long& t_act) {
-  (issue_layer<Epi, L>(smem_base, bar, tmem_base, desc_hi, nslots, r, act_parity0, act_parity1, t_act), ...);
 }
 
 template <class Epi>
@@ -251,13 +244,15 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // the biases of layer l -> the slot's staging row: one constant load + store per thread, between two barriers of
     // the slot's 256 threads (everybody has finished with the previous row / the new row is visible).  Called right
     // after a publish, i.e. while the slot would wait for its next accumulator anyway.
-    auto stage_bias = [&](int l) {
+    // `v` is this thread's element of the row, fetched EARLY (before the epilogue that precedes the staging) from the
+    // packed buffer's fp32 tail in global memory: coalesced and L2-resident, where 256 DIFFERENT constant-bank
+    // addresses per slot serialise in the constant cache (~1,000 cycles per staged row).
+    const uint32_t bias_t = threadIdx.x & 255u;
+    auto fetch_bias = [&](int l) -> float { return Epi::kStageBias ? __ldg(c.gf + kF32Bias + l * 256 + (int)bias_t) : 0.f; };
+    auto stage_bias = [&](float v) {
       if (!Epi::kStageBias) return;
       slot_barrier(slot);
-      const uint32_t t = threadIdx.x & 255u;
-      // from the packed buffer's fp32 tail in global memory (coalesced, L2-resident): 256 DIFFERENT constant-bank
-      // addresses per slot serialise in the constant cache (~1,000 cycles per staged row)
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + t * 4u), "f"(__ldg(c.gf + kF32Bias + l * 256 + (int)t)) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + bias_t * 4u), "f"(v) : "memory");
       slot_barrier(slot);
     };
     // before overwriting A[slot] / E[slot]: the bulk store of the previous image must have read it
@@ -276,9 +271,10 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       reclaim();
       long long tq0 = 0;
       if constexpr (Epi::kHasDbg && kDevBuild) tq0 = clock64();
+      const float bias0 = fetch_bias(0);
       Epi::begin_tile(p, st, c);
       publish(true);
-      stage_bias(0);
+      stage_bias(bias0);
       if constexpr (Epi::kHasDbg && kDevBuild) t_pro += clock64() - tq0;
       for (int l = 0; l < Epi::kNumLayers; ++l) {
         Epi::prefetch(p, st, c, l);  // global loads that do not depend on the accumulator
@@ -289,6 +285,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         long long tq1 = 0;
         if constexpr (Epi::kHasDbg && kDevBuild) { tq1 = clock64(); t_accw += tq1 - tq0; }
         reclaim();
+        const float bias_next = fetch_bias(l + 1 < Epi::kNumLayers ? l + 1 : l);
         Epi::layer(p, st, c, l);
         if (Epi::kBulkStore || l + 1 < Epi::kNumLayers) publish(l + 1 < Epi::kNumLayers);
         if constexpr (Epi::kHasDbg && kDevBuild) {
@@ -299,7 +296,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
             atomicAdd(p.dbg_counters + 32 + l, (unsigned long long)(tq1 - tq0));
           }
         }
-        if (l + 1 < Epi::kNumLayers) stage_bias(l + 1);
+        if (l + 1 < Epi::kNumLayers) stage_bias(bias_next);
         Epi::after_publish(p, st, c, l);
       }
     }
@@ -374,10 +371,10 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // peer CTA: nothing to issue (its MMAs are issued by the leader, its TMA signals the leader)
   } else {
     // ================================ leader CTA: MMA issuer ================================
-    // The whole warp walks the (compile-time unrolled) schedule convergently; one elected lane issues the tcgen05
-    // instructions.
+    // The whole warp walks the schedule convergently (one unrolled copy of the issue code per layer class); one
+    // elected lane issues the tcgen05 instructions.
     MmaRing ring{0u, 0u};
-    uint32_t act_parity0 = 0, act_parity1 = 0;
+    uint32_t act_parity[2] = {0u, 0u};
     long long t_act = 0;
 #ifdef NB200_DEV
     const long long t_begin = clock64();
@@ -385,8 +382,14 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);  // LBO/SBO/version/swizzle bits
     for (int64_t pr = 0; pr * Epi::kSlots < my_pt; ++pr) {
       const int nslots = (Epi::kSlots == 2 && my_pt - 2 * pr >= 2) ? 2 : 1;
-      issue_layers<Epi>(std::make_integer_sequence<int, Epi::kNumLayers>{}, smem_base, bar, tmem_base, desc_hi, nslots, ring,
-                        act_parity0, act_parity1, t_act);
+#pragma unroll 1
+      for (int l = 0; l < Epi::kNumLayers; ++l) {
+        const int rep = sched_class_rep<Epi::kSched>(l);
+        if (rep == 0) issue_layer<Epi, 0>(smem_base, bar, tmem_base, desc_hi, nslots, l, ring, act_parity, t_act);
+        else if (rep == 1) issue_layer<Epi, 1>(smem_base, bar, tmem_base, desc_hi, nslots, l, ring, act_parity, t_act);
+        else if (Epi::kSched != kSchedBwd && rep == 5) issue_layer<Epi, 5>(smem_base, bar, tmem_base, desc_hi, nslots, l, ring, act_parity, t_act);
+        else if (Epi::kSched != kSchedBwd) issue_layer<Epi, 9>(smem_base, bar, tmem_base, desc_hi, nslots, l, ring, act_parity, t_act);
+      }
     }
 #ifdef NB200_DEV
     if constexpr (Epi::kHasDbg && kDevBuild) {
