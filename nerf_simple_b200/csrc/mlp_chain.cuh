@@ -251,9 +251,9 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     auto fetch_bias = [&](int l) -> float { return Epi::kStageBias ? __ldg(c.gf + kF32Bias + l * 256 + (int)bias_t) : 0.f; };
     auto stage_bias = [&](float v) {
       if (!Epi::kStageBias) return;
-      slot_barrier(slot);
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + bias_t * 4u), "f"(v) : "memory");
-      slot_barrier(slot);
+      if (Epi::kSlots == 2) slot_barrier(slot); else asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (Epi::kSlots == 2 || threadIdx.x < 256u) asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.b_img + bias_t * 4u), "f"(v) : "memory");
+      if (Epi::kSlots == 2) slot_barrier(slot); else asm volatile("bar.sync 1, 512;" ::: "memory");
     };
     // before overwriting A[slot] / E[slot]: the bulk store of the previous image must have read it
     auto reclaim = [&]() {
@@ -263,6 +263,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
       }
       first_step = false;
     };
+    Epi::init_slot(c);   // once per kernel, by the slot's 256 threads
     for (int64_t k = slot; k < my_pt; k += Epi::kSlots) {
       c.tile = 2 * (cid + k * C) + rank;
       // the delta chain walks the tiles in REVERSE: the forward pass wrote the saved activations of the last
@@ -666,6 +667,7 @@ struct FwdEpi {
     bool row_valid;
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd; }
+  __device__ static void init_slot(const TileCtx&) {}
 
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
 
@@ -852,7 +854,7 @@ struct FwdEpi3 {
   static constexpr bool kHasDbg = false;
   static constexpr bool kBulkStore = false;
   static constexpr int kSched = kSchedFwd3;
-  static constexpr bool kStageBias = false;
+  static constexpr bool kStageBias = true;
   static constexpr int kSlots = 1;
   static constexpr int kNumLayers = kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
@@ -863,6 +865,7 @@ struct FwdEpi3 {
     bool row_valid;
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd3; }
+  __device__ static void init_slot(const TileCtx&) {}
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
   __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
   __device__ static void store_tile(const Params&, const TileCtx&, int) {}
@@ -896,21 +899,23 @@ struct FwdEpi3 {
     const uint32_t a_hi = c.a_img, a_lo = c.a_img + kABytes;
     if (ml < 9) {
       const int cbase = c.part * 64;
-      const float* b = c.cf + kF32Bias + ml * 256;
       const float* ws = c.cf + kF32WSig;
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int col0 = cbase + q * 16;
         uint32_t a[16];
+        float4 bq[4];
         tmem_ld16(c.t_lane + col0, a);
+        load_bias16(c, col0, bq);      // staged bias row of this layer (shared memory), under the TMEM load
         tmem_ld_wait();
         const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float x[8];
+          const float b[8] = {bq[2 * j].x, bq[2 * j].y, bq[2 * j].z, bq[2 * j].w, bq[2 * j + 1].x, bq[2 * j + 1].y, bq[2 * j + 1].z, bq[2 * j + 1].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            x[e] = __uint_as_float(a[8 * j + e]) + b[col0 + 8 * j + e];
+            x[e] = __uint_as_float(a[8 * j + e]) + b[e];
             if (ml != 8) x[e] = fmaxf(x[e], 0.f);                        // layers_2 has no activation (utils/nets.py:41)
             if (ml == 7) st.sigma = fmaf(x[e], ws[col0 + 8 * j + e], st.sigma);   // sigma head reads h7 in fp32 (:40)
           }
@@ -929,15 +934,21 @@ struct FwdEpi3 {
       uint32_t a[32];
       tmem_ld32(c.t_lane + col0, a);
       tmem_ld_wait();
-      const float* b = c.cf + kF32Bias + 9 * 256 + col0;
       const float* w = c.cf + kF32WC1 + col0;
       float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float x = fmaxf(__uint_as_float(a[e]) + b[e], 0.f);
-        rgb[0] = fmaf(x, w[e], rgb[0]);
-        rgb[1] = fmaf(x, w[128 + e], rgb[1]);
-        rgb[2] = fmaf(x, w[256 + e], rgb[2]);
+      for (int q = 0; q < 2; ++q) {
+        float4 bq[4];
+        load_bias16(c, col0 + 16 * q, bq);
+        const float b[16] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w,
+                             bq[2].x, bq[2].y, bq[2].z, bq[2].w, bq[3].x, bq[3].y, bq[3].z, bq[3].w};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float x = fmaxf(__uint_as_float(a[16 * q + e]) + b[e], 0.f);
+          rgb[0] = fmaf(x, w[16 * q + e], rgb[0]);
+          rgb[1] = fmaf(x, w[128 + 16 * q + e], rgb[1]);
+          rgb[2] = fmaf(x, w[256 + 16 * q + e], rgb[2]);
+        }
       }
       const uint32_t xaddr = c.e_img + ((uint32_t)c.part * 128u + c.r) * 16u;
       if (c.part != 0) st_shared_v4(xaddr, __float_as_uint(rgb[0]), __float_as_uint(rgb[1]), __float_as_uint(rgb[2]), __float_as_uint(st.sigma));
@@ -976,6 +987,18 @@ struct DgradEpi {
   struct State { float4 g; uint4 mask; };
   __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
   __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
+  // The delta chain has no use for the encoding buffers: E[slot] holds w_sigma (floats 0..255) and color_fc.2's weight
+  // (256..639) for the whole kernel, read with warp-uniform LDS.128 instead of constant-bank loads.
+  __device__ static void init_slot(const TileCtx& c) {
+    for (uint32_t i = threadIdx.x & 255u; i < 640u; i += 256u)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.e_img + i * 4u), "f"(__ldg(c.gf + (i < 256u ? kF32WSig + (int)i : kF32WC1 + (int)(i - 256u)))) : "memory");
+    slot_barrier(c.slot);
+  }
+  __device__ static __forceinline__ float4 head_ld4(const TileCtx& c, uint32_t i) {   // i % 4 == 0, warp-uniform
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(c.e_img + i * 4u));
+    return v;
+  }
 
   // The ReLU mask of layer l is this thread's 16-byte row of the bit-mask tensor the forward pass wrote (one bit per
   // element instead of the 64 KB bf16 activation tile): ONE load per thread and layer, issued before the accumulator
@@ -996,7 +1019,6 @@ struct DgradEpi {
     // delta_c1 = (d_rgb @ Wc1) * (c1 > 0)   (color_fc.2 backward, 3 -> 128, CUDA cores)
     const uint2 cbits = __ldg(reinterpret_cast<const uint2*>(p.saved + mask_tensor_off(8, T) + (size_t)c.tile * 2048 +
                                                              ((size_t)(c.half * 128) + c.r) * 8));
-    const float* w = c.cf + kF32WC1;
     const uint32_t kb = (uint32_t)c.half;  // 128 columns: each half of the slot's threads takes 64
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1004,11 +1026,18 @@ struct DgradEpi {
       // 8 columns = pairs 4*(j&1) .. +3 of the 16-column step j/2; steps 0,1 in cbits.x, 2,3 in cbits.y
       const uint32_t field = ((j < 4 ? cbits.x : cbits.y) >> (16 * ((j >> 1) & 1))) & 0xFFFFu;
       const int k0 = 4 * (j & 1);
+      const uint32_t col = (uint32_t)(c.half * 64 + j * 8);
       float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int col = c.half * 64 + j * 8 + e;
-        x[e] = fmaf(st.g.z, w[256 + col], fmaf(st.g.y, w[128 + col], st.g.x * w[col]));
+      {
+        const float4 a0 = head_ld4(c, 256u + col), a1 = head_ld4(c, 256u + col + 4u);
+        x[0] = st.g.x * a0.x; x[1] = st.g.x * a0.y; x[2] = st.g.x * a0.z; x[3] = st.g.x * a0.w;
+        x[4] = st.g.x * a1.x; x[5] = st.g.x * a1.y; x[6] = st.g.x * a1.z; x[7] = st.g.x * a1.w;
+        const float4 b0 = head_ld4(c, 384u + col), b1 = head_ld4(c, 384u + col + 4u);
+        x[0] = fmaf(st.g.y, b0.x, x[0]); x[1] = fmaf(st.g.y, b0.y, x[1]); x[2] = fmaf(st.g.y, b0.z, x[2]); x[3] = fmaf(st.g.y, b0.w, x[3]);
+        x[4] = fmaf(st.g.y, b1.x, x[4]); x[5] = fmaf(st.g.y, b1.y, x[5]); x[6] = fmaf(st.g.y, b1.z, x[6]); x[7] = fmaf(st.g.y, b1.w, x[7]);
+        const float4 c0 = head_ld4(c, 512u + col), c1 = head_ld4(c, 512u + col + 4u);
+        x[0] = fmaf(st.g.z, c0.x, x[0]); x[1] = fmaf(st.g.z, c0.y, x[1]); x[2] = fmaf(st.g.z, c0.z, x[2]); x[3] = fmaf(st.g.z, c0.w, x[3]);
+        x[4] = fmaf(st.g.z, c1.x, x[4]); x[5] = fmaf(st.g.z, c1.y, x[5]); x[6] = fmaf(st.g.z, c1.z, x[6]); x[7] = fmaf(st.g.z, c1.w, x[7]);
       }
       const uint32_t w0 = pack_bf16x2(x[0], x[1]) & pair_mask_word(field, k0), w1 = pack_bf16x2(x[2], x[3]) & pair_mask_word(field, k0 + 1),
                      w2 = pack_bf16x2(x[4], x[5]) & pair_mask_word(field, k0 + 2), w3 = pack_bf16x2(x[6], x[7]) & pair_mask_word(field, k0 + 3);
@@ -1033,14 +1062,15 @@ struct DgradEpi {
   template <bool kMasked, bool kSigma>
   __device__ static __forceinline__ void cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, uint32_t field, float gsig) {
     const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
-    const float* ws = c.cf + kF32WSig + col0;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float x[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        x[e] = __uint_as_float(a[8 * j + e]);
-        if (kSigma) x[e] = fmaf(gsig, ws[8 * j + e], x[e]);  // + d_sigma * w_sigma (sigma head reads h7)
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
+      if (kSigma) {   // + d_sigma * w_sigma (sigma head reads h7)
+        const float4 s0 = head_ld4(c, (uint32_t)(col0 + 8 * j)), s1 = head_ld4(c, (uint32_t)(col0 + 8 * j + 4));
+        x[0] = fmaf(gsig, s0.x, x[0]); x[1] = fmaf(gsig, s0.y, x[1]); x[2] = fmaf(gsig, s0.z, x[2]); x[3] = fmaf(gsig, s0.w, x[3]);
+        x[4] = fmaf(gsig, s1.x, x[4]); x[5] = fmaf(gsig, s1.y, x[5]); x[6] = fmaf(gsig, s1.z, x[6]); x[7] = fmaf(gsig, s1.w, x[7]);
       }
       uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
                w3 = pack_bf16x2(x[6], x[7]);

@@ -1,5 +1,6 @@
 """A/B of library builds on the render hot loop:  python scripts/ab_render.py lib_a.so lib_b.so ...
-Each library runs in its own process (NERF_B200_LIB); prints ms per 800x800x64 frame (device time, 8 frames)."""
+Each library runs in its own process (NERF_B200_LIB); prints ms per 800x800x64 frame (device time, 8 frames).
+AB_PRECISION=bf16x3 times the error-compensated mode."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
@@ -15,7 +16,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     torch.manual_seed(0)
     net = Nerf().cuda()
     poses = torch.stack(poses_to_render(4, -30, 30)).cuda()
-    rend = FrameRenderer(net, 800, 800, 800 / (2 * np.tan(0.6911112070083618 / 2)), N=64, seed=1, precision="bf16")
+    rend = FrameRenderer(net, 800, 800, 800 / (2 * np.tan(0.6911112070083618 / 2)), N=64, seed=1, precision=os.environ.get("AB_PRECISION", "bf16"))
     for i in range(3):
         rend.render_frame(poses, i)
     torch.cuda.synchronize()
