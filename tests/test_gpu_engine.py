@@ -65,3 +65,28 @@ def test_render_sharded_single_rank_is_the_frame():
         assert torch.equal(stitched.view(40, 40, 3), whole[0])
         rgb1, disp1 = render_sharded(_renderer(net), poses, 1, rank=0, world=1)
         assert torch.equal(rgb1.reshape(40, 40, 3), whole[0]) and torch.equal(disp1.reshape(40, 40), whole[1])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_chain_kernel_is_deterministic_over_many_tiles(fused):
+    """Twelve renders of the same 320x320x64 frame (51,200 tiles: ~170 per slot and CTA, both slots and the tail in
+    use) must be bit-identical: the epilogue warps of a slot share the staged bias row, the head-weight table that
+    lives in the free half of the posd rows, and the exchange rows of the colour layer, and a missing barrier or an
+    overlapping write between them shows up as run-to-run differences (found once this way: the posd zero padding
+    overwrote table entries written by faster threads)."""
+    from nerf_simple_b200.engine import FrameRenderer
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.xyz import poses_to_render
+    torch.manual_seed(0)
+    net = Nerf().cuda()
+    poses = torch.stack(poses_to_render(4, -30, 2)).cuda()
+    with torch.no_grad():
+        first = None
+        for _ in range(12):
+            r = FrameRenderer(net, 320, 320, 444.4, N=64, seed=5, precision="bf16", fused=fused)   # fresh Philox offsets
+            rgb, disp = r.render_frame(poses, 1)
+            if first is None:
+                first = (rgb.clone(), disp.clone())
+                assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(disp).all())
+            else:
+                assert torch.equal(rgb, first[0]) and torch.equal(disp, first[1])
