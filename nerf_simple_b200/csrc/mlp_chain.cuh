@@ -229,7 +229,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     uint32_t acc_parity = 0, free_parity = 0;
     typename Epi::State st;
     bool first_step = true;
-    long long t_epi = 0, t_accw = 0, t_pro = 0;
+    long long t_epi = 0, t_accw = 0, t_pro = 0, t_reclaim = 0, t_after = 0, t_stage = 0;
     // hand a finished tile image to the MMA warp (leader's act barrier) and, in the training kernels, to this slot's
     // store warp; `to_mma` is false after the last layer of a tile
     auto publish = [&](bool to_mma) {
@@ -286,6 +286,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         long long tq1 = 0;
         if constexpr (Epi::kHasDbg && kDevBuild) { tq1 = clock64(); t_accw += tq1 - tq0; }
         reclaim();
+        if constexpr (Epi::kHasDbg && kDevBuild) t_reclaim += clock64() - tq1;
         const float bias_next = fetch_bias(l + 1 < Epi::kNumLayers ? l + 1 : l);
         Epi::layer(p, st, c, l);
         if (Epi::kBulkStore || l + 1 < Epi::kNumLayers) publish(l + 1 < Epi::kNumLayers);
@@ -297,8 +298,13 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
             atomicAdd(p.dbg_counters + 32 + l, (unsigned long long)(tq1 - tq0));
           }
         }
+        long long tq3 = 0;
+        if constexpr (Epi::kHasDbg && kDevBuild) tq3 = clock64();
         if (l + 1 < Epi::kNumLayers) stage_bias(bias_next);
+        long long tq4 = 0;
+        if constexpr (Epi::kHasDbg && kDevBuild) { tq4 = clock64(); t_stage += tq4 - tq3; }
         Epi::after_publish(p, st, c, l);
+        if constexpr (Epi::kHasDbg && kDevBuild) t_after += clock64() - tq4;
       }
     }
     if constexpr (Epi::kHasDbg && kDevBuild) {
@@ -306,6 +312,9 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
         atomicAdd(p.dbg_counters + 4, (unsigned long long)t_epi);
         atomicAdd(p.dbg_counters + 5, (unsigned long long)t_accw);
         atomicAdd(p.dbg_counters + 6, (unsigned long long)t_pro);
+        atomicAdd(p.dbg_counters + 12, (unsigned long long)t_reclaim);
+        atomicAdd(p.dbg_counters + 13, (unsigned long long)t_stage);
+        atomicAdd(p.dbg_counters + 14, (unsigned long long)t_after);
       }
     }
     if (Epi::kBulkStore && !first_step) mbar_wait(bar + kB_StoreFree + 8 * slot, free_parity, 501);   // last store read its image

@@ -503,8 +503,8 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
     if (!ctr) { cudaMalloc(&ctr, 512); cudaMemset(ctr, 0, 512); }
     unsigned long long h[64];
     cudaMemcpy(h, ctr, 512, cudaMemcpyDeviceToHost);   // counters of the previous launch (debug only; syncs)
-    printf("nb200 dbg: mma-warp cycles wait_act=%llu total=%llu | epilogue warp 0: layers=%llu wait_acc=%llu prologue=%llu | producer wait_empty=%llu\n",
-           h[0], h[3], h[4], h[5], h[6], h[7]);
+    printf("nb200 dbg: mma-warp cycles wait_act=%llu total=%llu | epilogue warp 0: layers=%llu wait_acc=%llu prologue=%llu | producer wait_empty=%llu | epilogue warp 0: reclaim (inside layers)=%llu stage_bias=%llu after_publish=%llu\n",
+           h[0], h[3], h[4], h[5], h[6], h[7], h[12], h[13], h[14]);
     printf("nb200 dbg: epilogue warp 0 per layer, busy | wait_acc (share of total):");
     for (int l = 0; l < 10; ++l) printf(" L%d %.1f|%.1f", l, 100.0 * (double)h[16 + l] / (double)(h[3] ? h[3] : 1), 100.0 * (double)h[32 + l] / (double)(h[3] ? h[3] : 1));
     printf("\n");
