@@ -10,15 +10,22 @@
 //   warps 0-7 / 8-15 : prologue + epilogue of slot 0 / 1.  Two warps share each TMEM lane group:
 //                      thread (warp%4)*32+lane <-> sample row <-> TMEM lane, warps 4-7 of a slot take
 //                      the upper half of the accumulator columns (the epilogue is the critical path:
-//                      it must finish inside the 2048 cycles the other slot's MMAs take)
-//   warp  16         : weight producer (TMA bulk copy of this CTA's half slab)
-//   warp  17         : leader CTA: MMA issuer.  peer CTA: forwards "my half slab landed" to the leader.
+//                      it must finish inside the 2048 cycles the other slot's MMAs take).  Serving ONE slot at a
+//                      time with all 16 warps (64 columns per thread) was measured and is slower.
+//   warp  16         : weight producer (TMA tensor-map copy of this CTA's half slab); walks the slab table in the
+//                      constant bank.  It is never late: the MMA warp's weight waits do not block.
+//   warp  17         : leader CTA: MMA issuer, walking a COMPILE-TIME schedule (one unrolled copy of the issue code
+//                      per layer class, runtime slot and ring position).  peer CTA: idle.
 //   warps 18, 19     : training kernels only: bulk-store issuer of slot 0 / 1.  The epilogue warps hand a finished
 //                      tile image over through an mbarrier (one arrive per warp) and get the buffer back through
 //                      another one, instead of two 256-thread bar.syncs and a serial leader thread per layer.
 //
 // The same skeleton runs the forward chain (FwdEpi) and the backward delta chain (DgradEpi); they
 // differ only in the slab schedule and in what the epilogue warps do with each accumulator.
+//
+// Shared memory (231,680 B, 1 KB aligned): A[2] 2 x 64 KB activation tiles | E[2] 2 x 16 KB encodings (posx, later
+// posd + the head-weight table in the free half of its rows) | 4 x 16 KB weight ring | 256 B barriers | 2 x 1 KB
+// staged bias rows.  The epilogue issues no constant-bank loads: they were its bottleneck (ADU / MIO path).
 constexpr uint32_t kC_A = 0, kC_E = 2 * kABytes, kC_W = kC_E + 2 * kEBytes;
 constexpr int kCStages = 4;
 constexpr uint32_t kCStageBytes = 16384;
