@@ -196,6 +196,15 @@ class Trainer:
         self._packed_buf = (torch.empty(lib.nb200_packed_weights_bytes(self.precision), dtype=torch.uint8, device=self.device)
                             if self.precision == _lib.BF16 else None)
         self.use_graph = bool(use_graph) and self.precision == _lib.BF16 and self.N % 4 == 0 and self.N <= 1024
+        # why the step is NOT one CUDA-graph replay, when it is not (the eager path computes the same numbers, with
+        # ~14 launches of host overhead per step): readable by the caller instead of a silent fallback
+        self.graph_off_reason = (None if self.use_graph else
+                                 "use_graph=False" if not use_graph else
+                                 "precision is not bf16 (the fp32 step is ~65 launches, not captured)" if self.precision != _lib.BF16 else
+                                 f"N={self.N}: the device-resident sampler state needs N % 4 == 0 and N <= 1024")
+        if use_graph and not self.use_graph:
+            import warnings
+            warnings.warn(f"nerf_simple_b200.Trainer: CUDA-graph replay is off ({self.graph_off_reason}); steps are launched eagerly")
         self._graphs, self.graph_error = {}, None
         self.launches = 0
         self.part_events = []

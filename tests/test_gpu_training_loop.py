@@ -240,3 +240,26 @@ def test_trainer_graph_replay_matches_eager():
     assert a[0] == b[0]                                    # identical first step (same kernels, nothing accumulated yet)
     assert np.abs(a - b).max() <= 2e-2 * a.max()           # wgrad accumulates with atomics: trajectories agree closely
     assert b[-5:].mean() < 0.5 * b[:3].mean()
+
+
+def test_trainer_says_why_the_graph_path_is_off():
+    """A step that cannot be one CUDA-graph replay (ragged N, fp32 mode) still trains, eagerly, and says so."""
+    import warnings
+    from nerf_simple_b200 import ops
+    from nerf_simple_b200.nets import Nerf
+    from nerf_simple_b200.trainer import Trainer
+    from nerf_simple_b200.xyz import poses_to_render
+    torch.manual_seed(0)
+    poses = torch.stack(poses_to_render(4, -30, 2)).cuda()
+    rays = ops.generate_rays(poses, 24, 24, 33.3)
+    gt = torch.sigmoid(rays[:, 3:6] * 3)
+    tr = Trainer(Nerf().cuda(), rays, gt, N=32, batch_size=256, precision="bf16")
+    assert tr.use_graph and tr.graph_off_reason is None
+    tr.close()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        tr = Trainer(Nerf().cuda(), rays, gt, N=30, batch_size=256, precision="bf16")       # N % 4 != 0
+    assert not tr.use_graph and "N=30" in tr.graph_off_reason and any("graph" in str(x.message) for x in w)
+    losses = [tr.step(sync_loss=True) for _ in range(6)]
+    assert all(np.isfinite(losses)) and not tr._graphs
+    tr.close()
