@@ -42,8 +42,6 @@ constexpr int kCProducerWarp = 16, kCMmaWarp = 17, kCStoreWarp0 = 18;
 constexpr uint32_t kB_WFull = 0, kB_WPeer = 32, kB_WEmpty = 64, kB_Act = 96, kB_Acc = 112, kB_Tmem = 128, kB_Written = 136,
                    kB_StoreFree = 152;
 
-__constant__ __align__(16) float c_f32[kConstSlots * kF32Floats];  // biases / head weights of the nets being run (slot per packed buffer, uploaded per call)
-
 struct TileCtx {
   int64_t tile;      // 128-row tile index
   int slot;          // which in-flight tile of the CTA
@@ -54,8 +52,7 @@ struct TileCtx {
   uint32_t r7s;      // (r & 7) << 4
   uint32_t a_img, e_img, t_lane;
   uint32_t b_img;    // the slot's staged bias row (shared memory)
-  const float* cf;   // this launch's slot of the constant bank
-  const float* gf;   // the same fp32 tail in global memory (packed buffer)
+  const float* gf;   // the net's fp32 tail (biases, head weights) in global memory: part of the packed buffer
 };
 __device__ __forceinline__ uint32_t sw_off(const TileCtx& c, uint32_t kb, uint32_t j) {
   return kb * 16384u + c.rowoff + ((j << 4) ^ c.r7s);
@@ -226,11 +223,6 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     c.e_img = smem_base + kC_E + slot * kEBytes;
     c.t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)slot * 256u;
     c.b_img = smem_base + kC_Bias + (uint32_t)slot * 1024u;
-#ifdef NB_PROBE_SLOT0
-    c.cf = c_f32;
-#else
-    c.cf = c_f32 + p.cslot * kF32Floats;
-#endif
     c.gf = reinterpret_cast<const float*>(p.packed + (Epi::kSched == kSchedFwd3 ? c_layout.f32_off3 : c_layout.f32_off));
     const uint32_t act_remote = mapa_shared(bar + kB_Act + 8 * slot, 0);  // leader's act_ready[slot]
     uint32_t acc_parity = 0, free_parity = 0;
@@ -430,7 +422,6 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
 struct FwdEpiParams {
   CUtensorMap tmap128, tmap64;  // packed weight image as [rows x 128 B], boxes of 128 / 64 rows
   int dbg;
-  int cslot;       // constant-bank slot holding this net's fp32 tail
   unsigned long long* dbg_counters;
   int in_mode;
   const float* in0;
@@ -915,7 +906,7 @@ struct FwdEpi3 {
     const uint32_t a_hi = c.a_img, a_lo = c.a_img + kABytes;
     if (ml < 9) {
       const int cbase = c.part * 64;
-      const float* ws = c.cf + kF32WSig;
+      const float* ws = c.gf + kF32WSig;   // (read-only global loads at warp-uniform addresses; this mode is not bound by them)
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int col0 = cbase + q * 16;
@@ -933,7 +924,12 @@ struct FwdEpi3 {
           for (int e = 0; e < 8; ++e) {
             x[e] = __uint_as_float(a[8 * j + e]) + b[e];
             if (ml != 8) x[e] = fmaxf(x[e], 0.f);                        // layers_2 has no activation (utils/nets.py:41)
-            if (ml == 7) st.sigma = fmaf(x[e], ws[col0 + 8 * j + e], st.sigma);   // sigma head reads h7 in fp32 (:40)
+          }
+          if (ml == 7) {   // sigma head reads h7 in fp32 (:40)
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(ws + col0 + 8 * j)), s1 = __ldg(reinterpret_cast<const float4*>(ws + col0 + 8 * j + 4));
+            st.sigma = fmaf(x[0], s0.x, st.sigma); st.sigma = fmaf(x[1], s0.y, st.sigma); st.sigma = fmaf(x[2], s0.z, st.sigma);
+            st.sigma = fmaf(x[3], s0.w, st.sigma); st.sigma = fmaf(x[4], s1.x, st.sigma); st.sigma = fmaf(x[5], s1.y, st.sigma);
+            st.sigma = fmaf(x[6], s1.z, st.sigma); st.sigma = fmaf(x[7], s1.w, st.sigma);
           }
           uint32_t h[4], l[4];
 #pragma unroll
@@ -950,20 +946,24 @@ struct FwdEpi3 {
       uint32_t a[32];
       tmem_ld32(c.t_lane + col0, a);
       tmem_ld_wait();
-      const float* w = c.cf + kF32WC1 + col0;
+      const float4* w4 = reinterpret_cast<const float4*>(c.gf + kF32WC1 + col0);   // color_fc.2's weight, rows 128 floats apart
       float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         float4 bq[4];
         load_bias16(c, col0 + 16 * q, bq);
-        const float b[16] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w,
-                             bq[2].x, bq[2].y, bq[2].z, bq[2].w, bq[3].x, bq[3].y, bq[3].z, bq[3].w};
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float x = fmaxf(__uint_as_float(a[16 * q + e]) + b[e], 0.f);
-          rgb[0] = fmaf(x, w[16 * q + e], rgb[0]);
-          rgb[1] = fmaf(x, w[128 + 16 * q + e], rgb[1]);
-          rgb[2] = fmaf(x, w[256 + 16 * q + e], rgb[2]);
+        for (int g = 0; g < 4; ++g) {   // 4 columns at a time
+          const float b[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
+          float x[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = fmaxf(__uint_as_float(a[16 * q + 4 * g + e]) + b[e], 0.f);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float4 wv = __ldg(w4 + k * 32 + 4 * q + g);
+            rgb[k] = fmaf(x[0], wv.x, rgb[k]); rgb[k] = fmaf(x[1], wv.y, rgb[k]);
+            rgb[k] = fmaf(x[2], wv.z, rgb[k]); rgb[k] = fmaf(x[3], wv.w, rgb[k]);
+          }
         }
       }
       const uint32_t xaddr = c.e_img + ((uint32_t)c.part * 128u + c.r) * 16u;
@@ -978,8 +978,8 @@ struct FwdEpi3 {
           acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }
         if (st.row_valid)
-          reinterpret_cast<float4*>(p.out)[st.m_raw] = make_float4(acc.x + c.cf[kF32BC1], acc.y + c.cf[kF32BC1 + 1], acc.z + c.cf[kF32BC1 + 2],
-                                                                   acc.w + c.cf[kF32BSig]);   // (r,g,b,sigma), utils/nets.py:43
+          reinterpret_cast<float4*>(p.out)[st.m_raw] = make_float4(acc.x + __ldg(c.gf + kF32BC1), acc.y + __ldg(c.gf + kF32BC1 + 1), acc.z + __ldg(c.gf + kF32BC1 + 2),
+                                                                   acc.w + __ldg(c.gf + kF32BSig));   // (r,g,b,sigma), utils/nets.py:43
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");   // the encoding buffers may be rewritten for the next tile
     }

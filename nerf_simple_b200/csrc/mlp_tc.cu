@@ -63,7 +63,6 @@ struct PackedLayout {
 };
 constexpr int kF32Bias = 0, kF32WSig = 2560, kF32BSig = 2816, kF32WC1 = 2820, kF32BC1 = 3204,
               kF32Floats = 3264;
-constexpr int kConstSlots = 4;   // constant-bank copies of the fp32 tail (4 x 13 KB): concurrent nets never share one
 
 __constant__ __align__(16) PackedLayout c_layout;
 static PackedLayout h_layout;
@@ -391,34 +390,10 @@ static int ensure_attr(bool DeviceState::*which, F&& set) {
   return NB200_OK;
 }
 
-// Biases / head weights of the net being run go to the constant bank (stream-ordered D2D copy in front of the
-// launch).  The bank holds kConstSlots copies, assigned per (device, packed buffer): nets that run concurrently
-// from different streams or threads (coarse + fine, two trainers) use different slots and cannot overwrite each
-// other's biases; a slot is recycled (round robin) only when more than kConstSlots packed buffers are in use on a
-// device, and then only stream order protects it -- NB200_ERR_UNSUPPORTED is not raised for that, it is documented.
-struct ConstSlotEntry { const void* packed; int dev; };
-static ConstSlotEntry g_slots[kConstSlots];
-static int g_slot_next = 0;
-static int upload_consts(const void* packed, cudaStream_t s, int* slot_out, int x3 = 0) {
-  int dev = 0;
-  NB_TRY_RC(current_device(&dev));
-  int slot = -1;
-  {
-    std::lock_guard<std::mutex> lock(g_mu);
-    for (int i = 0; i < kConstSlots; ++i)
-      if (g_slots[i].packed == packed && g_slots[i].dev == dev) slot = i;
-    if (slot < 0) {
-      slot = g_slot_next;
-      g_slot_next = (g_slot_next + 1) % kConstSlots;
-      g_slots[slot].packed = packed; g_slots[slot].dev = dev;
-    }
-  }
-  NB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_f32, reinterpret_cast<const uint8_t*>(packed) + (x3 ? h_layout.f32_off3 : h_layout.f32_off),
-                                        kF32Floats * sizeof(float), (size_t)slot * kF32Floats * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, s));
-  *slot_out = slot;
-  return NB200_OK;
-}
+// Biases and head weights are read from the packed buffer's fp32 tail in global memory (staged through shared memory
+// by the kernels): nothing per-net lives in the constant bank, so any number of nets can run concurrently from
+// different streams or threads (coarse + fine, two trainers) without sharing state, and a launch needs no copy in
+// front of it.
 
 // Tensor maps over the packed weight image (plain [rows x 64 bf16] view, no TMA swizzle: the image
 // is pre-swizzled), cached per packed buffer.  cuTensorMapEncodeTiled is fetched through the runtime
@@ -490,7 +465,6 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   }));
   const int64_t T = saved ? train_tiles(M) : ceil_div64(M, kTileM);
   FwdEpiParams p;
-  NB_TRY_RC(upload_consts(packed, s, &p.cslot));
   TmapPair tm;
   NB_TRY_RC(get_tmaps(packed, &tm));
   p.tmap128 = tm.m128; p.tmap64 = tm.m64;
@@ -539,7 +513,6 @@ int tc_forward_x3(int in_mode, const float* in0, const float* in1, int64_t M, in
   const int64_t T = ceil_div64(M, kTileM);
   FwdEpiParams p;
   memset(&p, 0, sizeof(p));
-  NB_TRY_RC(upload_consts(packed, s, &p.cslot, 1));
   TmapPair tm;
   NB_TRY_RC(get_tmaps(packed, &tm, 1));
   p.tmap128 = tm.m128; p.tmap64 = tm.m64;
@@ -571,7 +544,6 @@ int tc_render(const float* rays, const float* poses, int H, int W, float f, int6
   const int64_t M = B * N, T = ceil_div64(M, kTileM);
   FwdEpiParams p;
   memset(&p, 0, sizeof(p));
-  NB_TRY_RC(upload_consts(packed, s, &p.cslot));
   TmapPair tm;
   NB_TRY_RC(get_tmaps(packed, &tm));
   p.tmap128 = tm.m128; p.tmap64 = tm.m64;
@@ -608,7 +580,6 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   bp.M = M; bp.num_tiles = T; bp.packed = reinterpret_cast<const uint8_t*>(packed); bp.saved = sv;
   bp.d_out = d_out; bp.dscr = ds;
   {
-    NB_TRY_RC(upload_consts(packed, s, &bp.cslot));
     TmapPair tm;
     NB_TRY_RC(get_tmaps(packed, &tm));
     bp.tmap128 = tm.m128; bp.tmap64 = tm.m64;

@@ -21,7 +21,6 @@ __host__ __device__ __forceinline__ size_t delta_tensor_off(int t, int64_t num_t
 struct BwdParams {
   CUtensorMap tmap128, tmap64;
   int dbg;
-  int cslot;           // constant-bank slot holding this net's fp32 tail
   int64_t M;
   int64_t num_tiles;
   const uint8_t* packed;

@@ -206,8 +206,8 @@ def test_frame_to_u8_exact():
 
 
 def test_two_nets_on_two_streams_do_not_share_biases(golden_weights):
-    """Concurrent nets (coarse + fine on their own streams) each keep their biases: the constant-bank copy of the
-    fp32 tail is per packed buffer."""
+    """Concurrent nets (coarse + fine on their own streams) each keep their biases: the kernels read the fp32 tail
+    (biases, head weights) from the net's own packed buffer, nothing per-net is shared."""
     g = load_golden("case_train_b64_n64.npz")
     q = torch.from_numpy(g["query"]).cuda().repeat(64, 1)
     a = _net(golden_weights)
