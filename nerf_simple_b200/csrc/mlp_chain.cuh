@@ -564,9 +564,9 @@ __device__ __forceinline__ float4 tab_ld4(uint32_t e_img, uint32_t i) {   // i %
   return v;
 }
 
-// One hidden layer: accumulator (TMEM) + bias -> [ReLU] -> bf16 A operand of the next layer.  Each
-// thread converts the 128 columns of its half; ReLU is fused into the fp32->bf16x2 conversion
-// (cvt.rn.relu.bf16x2.f32) and the biases come from the constant bank.
+// 16 accumulator columns + their (staged) biases -> [ReLU] -> two 16-byte chunks of the next layer's bf16 A operand.
+// ReLU is fused into the fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), the biases are added two at a time
+// (add.f32x2).  NB_PROBE_* builds are timing probes with wrong results (scripts/build_variants.sh).
 template <bool kRelu, bool kSigma, bool kSave>
 __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)[16], int col0, const float4 (&bq)[4], float& sigma) {
   const uint32_t kb = (uint32_t)col0 >> 6, j0 = ((uint32_t)col0 >> 3) & 7u;
@@ -580,12 +580,8 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 #endif
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(a[8 * j + e]);
-#ifdef NB_SCALAR_BIAS
-    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-#else
     add_f32x2(x[0], x[1], b0.x, b0.y); add_f32x2(x[2], x[3], b0.z, b0.w);
     add_f32x2(x[4], x[5], b1.x, b1.y); add_f32x2(x[6], x[7], b1.z, b1.w);
-#endif
     if (kSigma) {  // sigma head reads the (ReLU'd, fp32) layers_1 output (utils/nets.py:40)
       const float4 s0 = tab_ld4(c.e_img, kTabWSig + (uint32_t)(col0 + 8 * j)), s1 = tab_ld4(c.e_img, kTabWSig + (uint32_t)(col0 + 8 * j + 4));
       const float ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -611,9 +607,7 @@ __device__ __forceinline__ void epi_cols16(const TileCtx& c, const uint32_t (&a)
 
 // One hidden layer: accumulator (TMEM) + bias -> [ReLU] -> bf16 A operand of the next layer.  Each
 // thread converts the 128 columns of its half in 16-column steps, with the TMEM load of the next
-// step in flight while the current one is converted (double buffer); ReLU is fused into the
-// fp32->bf16x2 conversion (cvt.rn.relu.bf16x2.f32), biases come from the constant bank and are
-// added two at a time (add.f32x2).
+// step in flight while the current one is converted (double buffer).
 #ifdef NB_PROBE_NOLDTM   // timing probe only (wrong results): no TMEM reads in the hidden-layer epilogue
 #define tmem_ld16(addr, arr) do { _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) arr[i_] = (addr) + (uint32_t)i_; } while (0)
 #endif
@@ -642,10 +636,10 @@ __device__ __forceinline__ void epi_hidden_h(const TileCtx& c, float& sigma) {
     epi_cols16<kRelu, kSigma, kSave>(c, a1, cbase + (q + 1) * 16, bq, sigma);
   }
 }
-// The column half is dispatched to a compile-time constant: the bias (and sigma-head weight) addresses are then
-// "uniform base + immediate", which ptxas serves through the uniform datapath (LDCU) instead of per-thread indexed
-// LDC.  The indexed loads, 8 per 16 columns, saturated the MIO/ADU path: 31 % of all warp stall samples of the
-// forward kernel sat on them (stall_mio), and removing the bias path altogether was worth 16 % of the frame time.
+// The column half is dispatched to a compile-time constant, so that the shared-memory addresses of the staged biases,
+// of the head-weight table and of the swizzled stores are "base + immediate".  (Biases used to be indexed constant-bank
+// loads, 8 LDC.64 per 16 columns: they saturated the MIO/ADU path -- 31 % of all warp stall samples of the forward
+// kernel sat on them -- and removing the bias path altogether was worth 16 % of the frame time)
 template <bool kRelu, bool kSigma, bool kSave>
 __device__ __forceinline__ void epi_hidden(const TileCtx& c, float& sigma) {
   if (c.half == 0) epi_hidden_h<kRelu, kSigma, kSave, 0>(c, sigma);
