@@ -43,11 +43,16 @@ enum {
 /* precision of the MLP path */
 enum {
   NB200_FP32 = 0, /* fp32 SIMT layer kernels; parity mode, max-abs err <= 1e-4 vs reference    */
-  NB200_BF16 = 1, /* fused tcgen05 kernel, bf16 operands + fp32 accumulate in TMEM; <= 1e-2    */
-  NB200_BF16X3 = 2 /* the same tcgen05 chain with error-compensated bf16 (hi/lo images of activations and
+  NB200_BF16 = 1, /* fused tcgen05 kernel, bf16 operands + fp32 accumulate in TMEM; <= 1e-2.
+                     layers_2 (utils/nets.py:41, no activation) is folded into color_fc.0 at pack time (the
+                     product of the two weights is formed in fp32): 9 tensor-core layers per sample instead of
+                     10; the backward un-folds the gradients of both layers exactly (chain rule).            */
+  NB200_BF16X3 = 2, /* the same tcgen05 chain with error-compensated bf16 (hi/lo images of activations and
                       weights, three MMA passes per K-block): fp32-class accuracy (<= 1e-4, also with weights
                       scaled x1.5) on the tensor cores.  Forward / inference only: nb200_mlp_forward with
                       saved == NULL; its packed buffer has its own size and layout. */
+  NB200_BF16_LAYERWISE = 3 /* NB200_BF16 without the fold: every layer of utils/nets.py:34-43 is its own
+                      tensor-core layer.  Same packed image, saved-tensor and scratch layouts as NB200_BF16. */
 };
 
 /* input mode of the MLP kernels */

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NERF_B200_LIB", os.path.join(_HERE, "libnerf_b200.so"))   # override: A/B builds
 
 OK = 0
-FP32, BF16, BF16X3 = 0, 1, 2
+FP32, BF16, BF16X3, BF16_LAYERWISE = 0, 1, 2, 3
+BF16_MODES = (BF16, BF16_LAYERWISE)   # the two tcgen05 bf16 chains: layers_2 folded into color_fc.0 (default) / layer by layer
 IN_POINTS, IN_RAYS = 0, 1
 TRAIN_STATE_BYTES = 32     # NB200_TRAIN_STATE_BYTES
 P2P_FLAG_WORDS = 32        # NB200_P2P_FLAG_WORDS

@@ -27,8 +27,8 @@ _state = {
 
 
 def set_precision(p: str):
-    if p not in ("bf16", "fp32", "bf16x3"):
-        raise ValueError("precision must be 'bf16', 'fp32' or 'bf16x3'")
+    if p not in ("bf16", "fp32", "bf16x3", "bf16_layerwise"):
+        raise ValueError("precision must be 'bf16', 'fp32', 'bf16x3' or 'bf16_layerwise'")
     _state["precision"] = p
 
 

@@ -17,24 +17,27 @@ size_t tc_scratch_bytes(int64_t M, int train);
 int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s);
 int tc_forward_x3(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed, float* out, cudaStream_t s);
 int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
-               float* out, void* saved, void* scratch, size_t scratch_bytes, cudaStream_t s);
+               float* out, void* saved, void* scratch, size_t scratch_bytes, int fold, cudaStream_t s);
 int tc_backward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
                 const float* d_out, const void* saved, float* const* G, void* scratch,
-                size_t scratch_bytes, cudaStream_t s);
+                size_t scratch_bytes, int fold, cudaStream_t s);
 int tc_render(const float* rays, const float* poses, int H, int W, float f, int64_t ray_begin, const float* ts, uint64_t seed,
               uint64_t offset, int64_t B, int N, float tn, float tf, const void* packed, float* rgb, float* disp, float* acc,
-              cudaStream_t s);
+              int fold, cudaStream_t s);
 }  // namespace nb200
+
+// the two tcgen05 bf16 modes share the packed image and the saved / scratch layouts; NB200_BF16 runs the folded chain
+static inline bool is_bf16(int precision) { return precision == NB200_BF16 || precision == NB200_BF16_LAYERWISE; }
 
 extern "C" {
 
 size_t nb200_packed_weights_bytes(int precision) {
-  return precision == NB200_BF16 ? nb200::tc_packed_bytes(0) : (precision == NB200_BF16X3 ? nb200::tc_packed_bytes(1) : 0);
+  return is_bf16(precision) ? nb200::tc_packed_bytes(0) : (precision == NB200_BF16X3 ? nb200::tc_packed_bytes(1) : 0);
 }
 
 int nb200_pack_weights(int precision, const float* const* params, void* packed, nb200_stream_t stream) {
   if (precision == NB200_FP32) return NB200_OK;
-  if (precision != NB200_BF16 && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
+  if (!is_bf16(precision) && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
   if (!params || !packed) return NB200_ERR_ARG;
   for (int i = 0; i < 24; ++i)
     if (!params[i]) return NB200_ERR_ARG;
@@ -43,16 +46,16 @@ int nb200_pack_weights(int precision, const float* const* params, void* packed, 
 
 size_t nb200_mlp_saved_bytes(int precision, int64_t M) {
   if (M < 0 || precision == NB200_BF16X3) return 0;   // bf16x3 is an inference mode
-  return precision == NB200_BF16 ? nb200::tc_saved_bytes(M) : nb200::fp32_saved_bytes(M);
+  return is_bf16(precision) ? nb200::tc_saved_bytes(M) : nb200::fp32_saved_bytes(M);
 }
 
 size_t nb200_mlp_scratch_bytes(int precision, int64_t M, int train) {
   if (M < 0 || precision == NB200_BF16X3) return 0;
-  return precision == NB200_BF16 ? nb200::tc_scratch_bytes(M, train) : nb200::fp32_scratch_bytes(M, train);
+  return is_bf16(precision) ? nb200::tc_scratch_bytes(M, train) : nb200::fp32_scratch_bytes(M, train);
 }
 
 static int check_common(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N) {
-  if (precision != NB200_FP32 && precision != NB200_BF16 && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
+  if (precision != NB200_FP32 && !is_bf16(precision) && precision != NB200_BF16X3) return NB200_ERR_UNSUPPORTED;
   if (in_mode != NB200_IN_POINTS && in_mode != NB200_IN_RAYS) return NB200_ERR_ARG;
   if (M < 0) return NB200_ERR_ARG;
   if (in_mode == NB200_IN_RAYS && (N < 1 || M % N != 0)) return NB200_ERR_ARG;
@@ -78,7 +81,7 @@ int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float*
     return nb200::tc_forward_x3(in_mode, in0, in1, M, N, packed, out, nb200::as_stream(stream));
   }
   return nb200::tc_forward(in_mode, in0, in1, M, N, packed, out, saved, scratch, scratch_bytes,
-                           nb200::as_stream(stream));
+                           precision == NB200_BF16, nb200::as_stream(stream));
 }
 
 int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float* in1, int64_t M, int N,
@@ -100,12 +103,12 @@ int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float
   }
   if (!packed) return NB200_ERR_ARG;
   return nb200::tc_backward(in_mode, in0, in1, M, N, packed, d_out, saved, grads, scratch,
-                            scratch_bytes, nb200::as_stream(stream));
+                            scratch_bytes, precision == NB200_BF16, nb200::as_stream(stream));
 }
 
 static int check_render(int precision, int64_t B, int N, const void* packed, const float* rgb, const float* disp,
                         const float* acc) {
-  if (precision != NB200_BF16) return NB200_ERR_UNSUPPORTED;     // the fp32 parity mode keeps the three-kernel path
+  if (!is_bf16(precision)) return NB200_ERR_UNSUPPORTED;         // the fp32 parity mode keeps the three-kernel path
   if (B < 0 || N < 2) return NB200_ERR_ARG;
   if (N != 32 && N != 64 && N != 128) return NB200_ERR_UNSUPPORTED;  // whole rays per 128-sample tile
   if (B > 0 && (!packed || !rgb || !disp || !acc)) return NB200_ERR_ARG;
@@ -119,7 +122,7 @@ int nb200_render_rays(int precision, const float* rays, const float* ts, uint64_
   if (B == 0) return NB200_OK;
   if (!rays || ((uintptr_t)rays & 7)) return NB200_ERR_ARG;
   return nb200::tc_render(rays, nullptr, 0, 0, 0.f, 0, ts, seed, offset, B, N, tn, tf, packed, rgb, disp, acc,
-                          nb200::as_stream(stream));
+                          precision == NB200_BF16, nb200::as_stream(stream));
 }
 
 int nb200_render_camera(int precision, const float* poses, int P, int H, int W, float f, int64_t ray_begin, int64_t n_rays,
@@ -131,7 +134,7 @@ int nb200_render_camera(int precision, const float* poses, int P, int H, int W, 
   if (n_rays == 0) return NB200_OK;
   if (!poses) return NB200_ERR_ARG;
   return nb200::tc_render(nullptr, poses, H, W, f, ray_begin, nullptr, seed, offset, n_rays, N, tn, tf, packed, rgb, disp, acc,
-                          nb200::as_stream(stream));
+                          precision == NB200_BF16, nb200::as_stream(stream));
 }
 
 }  // extern "C"

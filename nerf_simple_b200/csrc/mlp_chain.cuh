@@ -75,7 +75,7 @@ constexpr bool kDevBuild = true;    // cycle counters of the MMA / epilogue / pr
 constexpr bool kDevBuild = false;
 #endif
 struct SlabC { int src, kb, n, ksteps, both_a; };
-constexpr int kSchedFwd = 0, kSchedBwd = 1, kSchedFwd3 = 2;
+constexpr int kSchedFwd = 0, kSchedBwd = 1, kSchedFwd3 = 2, kSchedFwdFold = 3;   // Fold: layers 0..7, then color_fc.0 as layer 8
 __host__ __device__ constexpr int sched_fwd_slabs(int l) { return l == 0 ? 1 : ((l == 5 || l == 9) ? 5 : 4); }
 __host__ __device__ constexpr SlabC sched_fwd_slab(int l, int s) {
   return l == 0 ? SlabC{1, 0, 256, 4, 0}
@@ -83,10 +83,12 @@ __host__ __device__ constexpr SlabC sched_fwd_slab(int l, int s) {
                           : (s < 4 ? SlabC{0, s, 256, 4, 0} : SlabC{1, 0, 256, 4, 0}));
 }
 template <int kSched> __host__ __device__ constexpr int sched_slabs(int l) {
-  return kSched == kSchedFwd ? sched_fwd_slabs(l) : (kSched == kSchedBwd ? (l == 0 ? 2 : 4) : 2 * sched_fwd_slabs(l));
+  return kSched == kSchedFwd ? sched_fwd_slabs(l)
+                             : (kSched == kSchedFwdFold ? sched_fwd_slabs(l >= 8 ? 9 : l) : (kSched == kSchedBwd ? (l == 0 ? 2 : 4) : 2 * sched_fwd_slabs(l)));
 }
 template <int kSched> __host__ __device__ constexpr SlabC sched_slab(int l, int s) {
   if (kSched == kSchedFwd) return sched_fwd_slab(l, s);
+  if (kSched == kSchedFwdFold) return sched_fwd_slab(l >= 8 ? 9 : l, s);
   if (kSched == kSchedBwd) return SlabC{0, s, 256, 4, 0};
   SlabC c = sched_fwd_slab(l, s >> 1);   // bf16x3: every forward slab twice, hi (against A_hi and A_lo) then lo (A_hi only)
   c.both_a = (s & 1) ? 0 : 1;
@@ -99,7 +101,7 @@ struct MmaRing { uint32_t stage, phase; };
 // one copy per layer and slot, was 100 KB of instructions and thrashed the instruction cache of the training kernels).
 // Class representatives: forward 0 | 1 (all plain 256x256 layers) | 5 (skip) | 9 (color_fc.0); delta chain 0 | 1.
 template <int kSched> __host__ __device__ constexpr int sched_class_rep(int l) {
-  return kSched == kSchedBwd ? (l == 0 ? 0 : 1) : ((l == 0 || l == 5 || l == 9) ? l : 1);
+  return kSched == kSchedBwd ? (l == 0 ? 0 : 1) : ((l == 0 || l == 5 || l == 9) ? l : ((kSched == kSchedFwdFold && l == 8) ? 9 : 1));
 }
 
 template <class Epi, int L, int S>
@@ -247,7 +249,7 @@ chain_kernel(const __grid_constant__ typename Epi::Params p) {
     // packed buffer's fp32 tail in global memory: coalesced and L2-resident, where 256 DIFFERENT constant-bank
     // addresses per slot serialise in the constant cache (~1,000 cycles per staged row).
     const uint32_t bias_t = threadIdx.x & 255u;
-    auto fetch_bias = [&](int l) -> float { return Epi::kStageBias ? __ldg(c.gf + kF32Bias + l * 256 + (int)bias_t) : 0.f; };
+    auto fetch_bias = [&](int l) -> float { return Epi::kStageBias ? __ldg(c.gf + kF32Bias + Epi::bias_row(l) * 256 + (int)bias_t) : 0.f; };
     auto stage_bias = [&](float v) {
       if (!Epi::kStageBias) return;
       if (Epi::kSlots == 2) slot_barrier(slot); else asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -649,17 +651,20 @@ __device__ __forceinline__ void epi_hidden(const TileCtx& c, float& sigma) {
 #undef tmem_ld16
 #endif
 
-template <bool kSave, bool kRender = false>
+// kFold: layers_2 folded into color_fc.0 (mlp_tc.cu, top): the chain has 9 layers, loop index 8 is MMA layer 9.
+template <bool kSave, bool kRender = false, bool kFold = false>
 struct FwdEpi {
   static_assert(!(kSave && kRender), "the fused render kernel is inference only");
   using Params = FwdEpiParams;
   static constexpr bool kHasDbg = true;
   static constexpr bool kBulkStore = kSave;  // training: finished tile images leave through TMA bulk stores
-  static constexpr int kSched = kSchedFwd;
+  static constexpr int kSched = kFold ? kSchedFwdFold : kSchedFwd;
   static constexpr bool kStageBias = true;
   static constexpr int kSlots = 2;
-  static constexpr int kNumLayers = kNumMmaLayers;
+  static constexpr int kNumLayers = kFold ? kNumFoldLayers : kNumMmaLayers;
   static constexpr bool kReverseTiles = false;
+  __device__ static constexpr int ml_of(int l) { return (kFold && l == 8) ? 9 : l; }                 // loop index -> MMA layer
+  __device__ static constexpr int bias_row(int l) { return (kFold && l == 8) ? kFoldBiasRow : l; }
   struct State {
     float v[6];
     float sigma;
@@ -667,7 +672,7 @@ struct FwdEpi {
     int64_t m_raw;
     bool row_valid;
   };
-  __device__ static const SlabDesc* slabs() { return c_layout.fwd; }
+  __device__ static const SlabDesc* slabs() { return kFold ? c_layout.fwdf : c_layout.fwd; }
   __device__ static void init_slot(const TileCtx&) {}
 
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
@@ -676,7 +681,8 @@ struct FwdEpi {
   // image was handed to the MMA warp and the store warp, from the bf16 image in shared memory: the epilogue warps of
   // this slot would otherwise idle until their next accumulator is ready, so the ~130 extra instructions per thread
   // and layer stay off the critical path (inside the epilogue they cost the kernel 11 %).
-  __device__ static void after_publish(const Params& p, State& st, const TileCtx& c, int ml) {
+  __device__ static void after_publish(const Params& p, State& st, const TileCtx& c, int l) {
+    const int ml = ml_of(l);
     if (ml == 5) {
       // posx has been consumed by the skip layer's MMAs: the encoding buffer now carries posd (27 -> 64) for color_fc.0,
       // plus the head-weight table in the free half of its rows.  Done here, behind the hand-off of h5, so that it
@@ -741,15 +747,17 @@ struct FwdEpi {
   }
 
   // one thread per slot, after the slot barrier: tile images shared -> global (saved activations)
-  __device__ static void store_tile(const Params& p, const TileCtx& c, int ml) {
+  __device__ static void store_tile(const Params& p, const TileCtx& c, int l) {
     const int64_t T = p.num_tiles;
+    const int ml = ml_of(l);
     if (ml == -1) tma_bulk_s2g(p.saved + saved_tensor_off(10, T) + (size_t)c.tile * 16384, c.e_img, 16384);        // posx
     else if (ml < 9) tma_bulk_s2g(p.saved + saved_tensor_off(ml, T) + (size_t)c.tile * 65536, c.a_img, 65536);    // h0..h7, g
     else tma_bulk_s2g(p.saved + saved_tensor_off(9, T) + (size_t)c.tile * 32768, c.a_img, 32768);                  // c1
     if (ml == 6) tma_bulk_s2g(p.saved + saved_tensor_off(11, T) + (size_t)c.tile * 16384, c.e_img, 16384);         // posd (encoded behind h5's hand-off)
   }
 
-  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int ml) {
+  __device__ static void layer(const Params& p, State& st, const TileCtx& c, int l) {
+    const int ml = ml_of(l);
     if (ml < 9) {
       if (ml == 7) epi_hidden<true, true, kSave>(c, st.sigma);
       else if (ml == 8) epi_hidden<false, false, kSave>(c, st.sigma);  // layers_2: no act.
@@ -870,6 +878,7 @@ struct FwdEpi3 {
     bool row_valid;
   };
   __device__ static const SlabDesc* slabs() { return c_layout.fwd3; }
+  __device__ static constexpr int bias_row(int l) { return l; }
   __device__ static void init_slot(const TileCtx&) {}
   __device__ static void prefetch(const Params&, State&, const TileCtx&, int) {}
   __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
@@ -989,6 +998,8 @@ struct FwdEpi3 {
 #define NB_DG_L2HINT 2   // bit 1: delta stores evict_first (511 -> 501 us).  bit 0 (mask prefetch evict_last, -6 us more) is off:
                           // the evict_last lines outlive the kernel and made the first render after training 2x slower
 #endif
+// kFold: delta_h7 = delta_c1 Wf in ONE layer (mlp_tc.cu, top): 8 MMA layers, loop index l is bl = l + 2.
+template <bool kFold>
 struct DgradEpi {
   using Params = BwdParams;
   static constexpr bool kHasDbg = false;
@@ -996,10 +1007,12 @@ struct DgradEpi {
   static constexpr int kSched = kSchedBwd;
   static constexpr bool kStageBias = false;
   static constexpr int kSlots = 2;
-  static constexpr int kNumLayers = 9;  // bl = 1..9
+  static constexpr int kNumLayers = kFold ? 8 : 9;  // bl = 1..9 (folded: 2..9)
+  static constexpr int kBl0 = kFold ? 2 : 1;        // bl of loop index 0
   static constexpr bool kReverseTiles = true;
   struct State { float4 g; uint4 mask; };
-  __device__ static const SlabDesc* slabs() { return c_layout.bwd; }
+  __device__ static const SlabDesc* slabs() { return kFold ? c_layout.bwdf : c_layout.bwd; }
+  __device__ static constexpr int bias_row(int l) { return l; }
   __device__ static void after_publish(const Params&, State&, const TileCtx&, int) {}
   // The delta chain has no use for the encoding buffers: E[slot] holds w_sigma (floats 0..255) and color_fc.2's weight
   // (256..639) for the whole kernel, read with warp-uniform LDS.128 instead of constant-bank loads.
@@ -1019,7 +1032,7 @@ struct DgradEpi {
   // wait, so its latency is off the epilogue's critical path (the per-thread loads of the activation tile used to
   // account for 25 % of the kernel's stall samples, and for 1.1 GB of DRAM reads per step).
   __device__ static void prefetch(const Params& p, State& st, const TileCtx& c, int l) {
-    const int bl = l + 1;       // masks with h_{9-bl}: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
+    const int bl = l + kBl0;    // masks with h_{9-bl}: bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
     if (bl >= 2)
       st.mask = __ldg(reinterpret_cast<const uint4*>(p.saved + mask_tensor_off(9 - bl, p.num_tiles) + (size_t)c.tile * 4096 +
                                                      ((size_t)(c.half * 128) + c.r) * 16));
@@ -1065,10 +1078,10 @@ struct DgradEpi {
 #if NB_DG_L2HINT & 2
     const uint64_t pol = l2_policy_evict_first();
     if (l == -1) tma_bulk_s2g_hint(p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768, c.a_img, 32768, pol);   // delta_c1
-    else tma_bulk_s2g_hint(p.dscr + delta_tensor_off(l + 1, T) + (size_t)c.tile * 65536, c.a_img, 65536, pol);
+    else tma_bulk_s2g_hint(p.dscr + delta_tensor_off(l + kBl0, T) + (size_t)c.tile * 65536, c.a_img, 65536, pol);
 #else
     if (l == -1) tma_bulk_s2g(p.dscr + delta_tensor_off(0, T) + (size_t)c.tile * 32768, c.a_img, 32768);   // delta_c1
-    else tma_bulk_s2g(p.dscr + delta_tensor_off(l + 1, T) + (size_t)c.tile * 65536, c.a_img, 65536);
+    else tma_bulk_s2g(p.dscr + delta_tensor_off(l + kBl0, T) + (size_t)c.tile * 65536, c.a_img, 65536);
 #endif
   }
 
@@ -1116,7 +1129,7 @@ struct DgradEpi {
 
   __device__ static void layer(const Params&, State& st, const TileCtx& c, int l) {
     // ReLU mask (bit per element, loaded in prefetch): bl=2 -> h7, ..., bl=9 -> h0; bl=1 yields delta_g (no activation)
-    const int bl = l + 1;
+    const int bl = l + kBl0;
     if (bl == 1) layer_t<false, false>(st, c);
     else if (bl == 2) layer_t<true, true>(st, c);
     else layer_t<true, false>(st, c);

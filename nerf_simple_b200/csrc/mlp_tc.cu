@@ -24,6 +24,18 @@ using namespace tc;
 // ------------------------------------------------------------------ packed weight image
 constexpr int kNumMmaLayers = 10;  // L0_0..L0_4, skip, L1_0, L1_1, layers_2, color_fc.0
 constexpr int kMaxSlabs = 48;
+// NB200_BF16 folds layers_2 into color_fc.0.  layers_2 has no activation (utils/nets.py:41-42), so
+//   color_fc.0(cat[layers_2(h7), posd]) = (Wc0[:, :256] Wg) h7 + Wc0[:, 256:] posd + (Wc0[:, :256] bg + bc0):
+// the folded weight Wf = Wc0[:, :256] Wg (128 x 256) and bias bf are formed in fp32 at pack time and rounded to bf16
+// once, so a sample costs 9 MMA layers instead of 10 (-11 % of the FLOPs) and `g` is never rounded to bf16.
+// Backward: delta_h7 = delta_c1 Wf (one 128 -> 256 layer instead of two), and with Gm = delta_c1^T h7 (128 x 256, ONE
+// wgrad item) the chain rule gives dWc0[:, :256] = Gm Wg^T + s bg^T, dWg = Wc0[:, :256]^T Gm, dbg = Wc0[:, :256]^T s,
+// dbc0 = s (s = column sums of delta_c1): two tiny fp32 GEMMs (fold_grads_kernel) replace the 256 x 256 wgrad item of
+// layers_2 and the HBM round trip of g and delta_g.  NB200_BF16_LAYERWISE keeps every layer of the reference as its
+// own MMA layer.
+constexpr int kNumFoldLayers = kNumMmaLayers - 1;
+constexpr int kLayerFold = 100;    // SlabDesc::layer of a slab packed from the folded fp32 weight in the packed buffer's tail
+constexpr int kFoldBiasRow = 10;   // bias row of the folded color_fc.0
 
 struct SlabDesc {
   uint32_t off;     // byte offset of the slab image in the packed buffer
@@ -52,7 +64,15 @@ struct PackedLayout {
   SlabDesc fwd[kMaxSlabs];
   int num_bwd;
   SlabDesc bwd[kMaxSlabs];  // dgrad chain: transposed weight images, 9 MMA layers
-  uint32_t f32_off;  // fp32 section: bias[10][256] | wsig[256] | bsig(+pad 4) | wc1[3][128] | bc1[3](+pad)
+  // folded chains: the tables of the 9-layer forward and the 8-layer delta chain (entries shared with fwd / bwd point
+  // at the same images), and the 6 slabs that exist only in the folded form (Wf: 4 forward + 2 transposed)
+  int num_fwdf;
+  SlabDesc fwdf[kMaxSlabs];
+  int num_bwdf;
+  SlabDesc bwdf[kMaxSlabs];
+  int num_fold;
+  SlabDesc fold[8];
+  uint32_t f32_off;  // fp32 section: bias[11][256] | wsig[256] | bsig(+pad 4) | wc1[3][128] | bc1[3](+pad) | fold tail
   uint32_t total_bytes;
   // NB200_BF16X3 (error-compensated bf16, forward only): its own packed buffer = per K-block a hi slab bf16(W) and a lo
   // slab bf16(W - bf16(W)), then the same fp32 tail
@@ -61,8 +81,11 @@ struct PackedLayout {
   uint32_t f32_off3;
   uint32_t total_bytes3;
 };
-constexpr int kF32Bias = 0, kF32WSig = 2560, kF32BSig = 2816, kF32WC1 = 2820, kF32BC1 = 3204,
-              kF32Floats = 3264;
+constexpr int kF32Bias = 0, kF32WSig = 2816, kF32BSig = 3072, kF32WC1 = 3076, kF32BC1 = 3460,
+              kF32Floats = 3520;
+// fold tail (bf16 image only): Wf [128][256] | Wg^T [256][256] | Wc0[:, :256] [128][256] | bg [256], all fp32
+constexpr int kF32Wf = kF32Floats, kF32WgT = kF32Wf + 128 * 256, kF32Wc0g = kF32WgT + 256 * 256, kF32Bg = kF32Wc0g + 128 * 256,
+              kF32FloatsFold = kF32Bg + 256;
 
 __constant__ __align__(16) PackedLayout c_layout;
 static PackedLayout h_layout;
@@ -137,8 +160,29 @@ static void build_layout() {
     h_layout.bwd[t.s - 1].last = 1;
   }
   h_layout.num_bwd = t.s;
-  h_layout.f32_off = t.off;
-  h_layout.total_bytes = t.off + kF32Floats * (uint32_t)sizeof(float);
+  // the slabs of the folded weight: forward image (n = c1 feature, k = h7 feature), then transposed for the delta chain
+  LayoutBuilder f;
+  f.arr = h_layout.fold; f.off = t.off; f.s = 0;
+  for (int kb = 0; kb < 4; ++kb) f.add(9, kLayerFold, 0, 128, kb * 64, 64, kHidden, 0, kb, 4);
+  for (int kb = 0; kb < 2; ++kb) f.add(2, kLayerFold, 1, 256, kb * 64, 64, kHidden, 0, kb, 4);
+  h_layout.num_fold = f.s;
+  {
+    int n = 0;
+    for (int i = 0; i < h_layout.num_fwd; ++i)
+      if (h_layout.fwd[i].ml < 8) h_layout.fwdf[n++] = h_layout.fwd[i];
+    for (int kb = 0; kb < 4; ++kb) h_layout.fwdf[n++] = h_layout.fold[kb];
+    h_layout.fwdf[n - 4].first = 1;
+    h_layout.fwdf[n++] = h_layout.fwd[h_layout.num_fwd - 1];   // color_fc.0 <- posd (last slab of the layer)
+    h_layout.num_fwdf = n;
+    n = 0;
+    for (int kb = 0; kb < 2; ++kb) h_layout.bwdf[n++] = h_layout.fold[4 + kb];
+    h_layout.bwdf[0].first = 1; h_layout.bwdf[1].last = 1;
+    for (int i = 0; i < h_layout.num_bwd; ++i)
+      if (h_layout.bwd[i].ml >= 3) h_layout.bwdf[n++] = h_layout.bwd[i];
+    h_layout.num_bwdf = n;
+  }
+  h_layout.f32_off = f.off;
+  h_layout.total_bytes = f.off + kF32FloatsFold * (uint32_t)sizeof(float);
   // bf16x3: every forward slab twice (hi: consumed with A_hi and A_lo; lo: with A_hi), in consumption order
   LayoutBuilder x;
   x.arr = h_layout.fwd3; x.off = 0; x.s = 0;
@@ -190,8 +234,12 @@ template <bool kX3>
 __global__ void __launch_bounds__(256) pack_slabs_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
   const int slab = (int)blockIdx.x / kPackSplit, part = (int)blockIdx.x % kPackSplit;
   const bool is_bwd = !kX3 && slab >= c_layout.num_fwd;
-  const SlabDesc d = kX3 ? c_layout.fwd3[slab] : (is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab]);
-  const float* W = P.p[2 * d.layer];
+  const bool is_fold = !kX3 && slab >= c_layout.num_fwd + c_layout.num_bwd;
+  const SlabDesc d = kX3 ? c_layout.fwd3[slab]
+                         : (is_fold ? c_layout.fold[slab - c_layout.num_fwd - c_layout.num_bwd]
+                                    : (is_bwd ? c_layout.bwd[slab - c_layout.num_fwd] : c_layout.fwd[slab]));
+  // the folded weight was written to the packed buffer's fp32 tail by fold_weights_kernel (same stream, before this kernel)
+  const float* W = is_fold ? reinterpret_cast<const float*>(packed + c_layout.f32_off) + kF32Wf : P.p[2 * d.layer];
   for (int item = part * blockDim.x + threadIdx.x; item < d.n * 8; item += blockDim.x * kPackSplit) {
     const int n = item >> 3, j = item & 7;
     uint32_t w[4];
@@ -216,6 +264,7 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(ParamPtrs P, float* __res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kF32Floats) return;
   float v = 0.f;
+  if (i >= kF32Bias + kFoldBiasRow * 256 && i < kF32WSig) return;   // the folded bias row belongs to fold_weights_kernel
   if (i < kF32WSig) {
     const int ml = i >> 8, j = i & 255;
     const int layer = mma_layer_of(ml);
@@ -231,6 +280,34 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(ParamPtrs P, float* __res
     v = P.p[2 * L_C1 + 1][i - kF32BC1];
   }
   f[i] = v;
+}
+
+// Folded weight and bias in fp32 (see the top of the file), plus the fp32 copies the gradient un-folding reads.
+// 65,536 threads; a 128 x 256 x 256 GEMM on CUDA cores is ~2 us of an optimizer step.
+__global__ void __launch_bounds__(256) fold_weights_kernel(ParamPtrs P, float* __restrict__ f) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Wc0 = P.p[2 * L_C0];
+  const float* Wg = P.p[2 * L_2];
+  const float* bg = P.p[2 * L_2 + 1];
+  constexpr int ldc = kHidden + kPosD;
+  if (t < 128 * 256) {
+    const int i = t >> 8, j = t & 255;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Wc0 + i * ldc + k), __ldg(Wg + k * kHidden + j), acc);
+    f[kF32Wf + t] = acc;
+    f[kF32Wc0g + t] = __ldg(Wc0 + i * ldc + j);
+  }
+  if (t < 256 * 256) f[kF32WgT + t] = __ldg(Wg + (t & 255) * kHidden + (t >> 8));   // [k][j] = Wg[j][k]
+  if (t < 256) {
+    f[kF32Bg + t] = __ldg(bg + t);
+    float acc = 0.f;
+    if (t < 128) {
+      acc = __ldg(P.p[2 * L_C0 + 1] + t);
+      for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Wc0 + t * ldc + k), __ldg(bg + k), acc);
+    }
+    f[kF32Bias + kFoldBiasRow * 256 + t] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------- tile geometry
@@ -315,6 +392,8 @@ static bool schedule_matches(const SlabDesc* tab, int num, int layers) {
 static bool check_schedules() {
   return schedule_matches<kSchedFwd>(h_layout.fwd, h_layout.num_fwd, kNumMmaLayers) &&
          schedule_matches<kSchedBwd>(h_layout.bwd, h_layout.num_bwd, 9) &&
+         schedule_matches<kSchedFwdFold>(h_layout.fwdf, h_layout.num_fwdf, kNumFoldLayers) &&
+         schedule_matches<kSchedBwd>(h_layout.bwdf, h_layout.num_bwdf, 8) &&
          schedule_matches<kSchedFwd3>(h_layout.fwd3, h_layout.num_fwd3, kNumMmaLayers);
 }
 
@@ -335,28 +414,66 @@ size_t tc_saved_bytes(int64_t M) { return (size_t)train_tiles(M) * kSavedTileByt
 // was 4x slower and left the CTAs holding them ~80 us behind the rest)
 constexpr int kPadPitchWide = 320, kPadPitchX = 64;
 constexpr size_t kPadC0 = 0, kPadSkip = kPadC0 + 128 * kPadPitchWide, kPadL00 = kPadSkip + 256 * kPadPitchWide,
-                 kPadFloats = kPadL00 + 256 * kPadPitchX;
+                 kPadFoldS = kPadL00 + 256 * kPadPitchX,   // folded chain: column sums of delta_c1 (128 floats)
+                 kPadFloats = kPadFoldS + 128;
 size_t tc_scratch_bytes(int64_t M, int train) {
   return train ? (size_t)train_tiles(M) * kDeltaTileBytes + kPadFloats * sizeof(float) : 0;
 }
 
 // grad[r, c] += pad[r, c] for the three padded images (one thread per padded float4 group)
+// (folded chain: columns 0..255 of the color_fc.0 image hold Gm = delta_c1^T h7, un-folded by fold_grads_kernel)
 __global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ pad, float* __restrict__ gC0,
-                                                        float* __restrict__ gSkip, float* __restrict__ gL00) {
+                                                        float* __restrict__ gSkip, float* __restrict__ gL00, int fold) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float index into the pad buffer
-  if (i >= (int)kPadFloats) return;
+  if (i >= (int)kPadFoldS) return;
   float* g; int r, c, ncols;
-  if (i < (int)kPadSkip) { r = i / kPadPitchWide; c = i - r * kPadPitchWide; g = gC0; ncols = kHidden + kPosD; }
+  if (i < (int)kPadSkip) { r = i / kPadPitchWide; c = i - r * kPadPitchWide; g = gC0; ncols = kHidden + kPosD; if (fold && c < kHidden) return; }
   else if (i < (int)kPadL00) { const int j = i - (int)kPadSkip; r = j / kPadPitchWide; c = j - r * kPadPitchWide; g = gSkip; ncols = kHidden + kPosX; }
   else { const int j = i - (int)kPadL00; r = j / kPadPitchX; c = j - r * kPadPitchX; g = gL00; ncols = kPosX; }
   if (c < ncols) g[(size_t)r * ncols + c] += pad[i];
+}
+
+// Folded chain: gradients of color_fc.0[:, :256], layers_2 and their biases from Gm = delta_c1^T h7 (pad image of
+// color_fc.0, columns 0..255) and s = column sums of delta_c1 (see the top of the file).  `f` = the packed buffer's
+// fp32 tail (Wg^T, Wc0[:, :256], bg as they were at pack time).  98,688 threads, ~17 MFLOP.
+__global__ void __launch_bounds__(256) fold_grads_kernel(const float* __restrict__ pad, const float* __restrict__ f,
+                                                         float* __restrict__ gC0, float* __restrict__ gbC0,
+                                                         float* __restrict__ gL2, float* __restrict__ gbL2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Gm = pad + kPadC0;
+  const float* sv = pad + kPadFoldS;
+  if (t < 128 * 256) {                       // dWc0[i, j] += sum_k Gm[i, k] Wg[j, k] + s[i] bg[j]
+    const int i = t >> 8, j = t & 255;
+    float acc = __ldg(sv + i) * __ldg(f + kF32Bg + j);
+#pragma unroll 8
+    for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Gm + i * kPadPitchWide + k), __ldg(f + kF32WgT + k * kHidden + j), acc);
+    gC0[i * (kHidden + kPosD) + j] += acc;
+  } else if (t < 128 * 256 + 256 * 256) {    // dWg[j, k] += sum_i Wc0[i, j] Gm[i, k]
+    const int u = t - 128 * 256, j = u >> 8, k = u & 255;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(f + kF32Wc0g + i * kHidden + j), __ldg(Gm + i * kPadPitchWide + k), acc);
+    gL2[j * kHidden + k] += acc;
+  } else if (t < 128 * 256 + 256 * 256 + 256) {   // dbg[j] += sum_i Wc0[i, j] s[i]
+    const int j = t - (128 * 256 + 256 * 256);
+    float acc = 0.f;
+    for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(f + kF32Wc0g + i * kHidden + j), __ldg(sv + i), acc);
+    gbL2[j] += acc;
+  } else if (t < 128 * 256 + 256 * 256 + 256 + 128) {
+    const int i = t - (128 * 256 + 256 * 256 + 256);
+    gbC0[i] += __ldg(sv + i);
+  }
 }
 
 int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s) {
   NB_TRY_RC(ensure_layout());
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = P[i];
-  const int nslabs = x3 ? h_layout.num_fwd3 : h_layout.num_fwd + h_layout.num_bwd;
+  const int nslabs = x3 ? h_layout.num_fwd3 : h_layout.num_fwd + h_layout.num_bwd + h_layout.num_fold;
+  if (!x3) {
+    fold_weights_kernel<<<256, 256, 0, s>>>(pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + h_layout.f32_off));
+    NB_LAUNCH_CHECK("fold_weights_kernel");
+  }
   if (x3) pack_slabs_kernel<true><<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
   else pack_slabs_kernel<false><<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
   NB_LAUNCH_CHECK("pack_slabs_kernel");
@@ -453,13 +570,17 @@ static int chain_grid(int64_t T) {
 }
 
 int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N, const void* packed,
-               float* out, void* saved, void*, size_t, cudaStream_t s) {
+               float* out, void* saved, void*, size_t, int fold, cudaStream_t s) {
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
   NB_TRY_RC(ensure_attr(&DeviceState::attr_fwd, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false, false, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<true, false, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
     return NB200_OK;
   }));
@@ -492,8 +613,12 @@ int tc_forward(int in_mode, const float* in0, const float* in1, int64_t M, int N
   p.out = out; p.saved = reinterpret_cast<uint8_t*>(saved);
   p.num_tiles = T;
   const int grid = chain_grid(T);
-  if (saved)
+  if (saved && fold)
+    chain_kernel<FwdEpi<true, false, true>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
+  else if (saved)
     chain_kernel<FwdEpi<true>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
+  else if (fold)
+    chain_kernel<FwdEpi<false, false, true>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
   else
     chain_kernel<FwdEpi<false>><<<grid, kCThreads, kCSmemLaunch, s>>>(p);
   NB_LAUNCH_CHECK("chain_kernel<FwdEpi>");
@@ -533,11 +658,13 @@ int tc_forward_x3(int in_mode, const float* in0, const float* in1, int64_t M, in
 // ts == nullptr: Philox sample depths (same stream as nb200_stratified_ts with the same seed/offset).
 int tc_render(const float* rays, const float* poses, int H, int W, float f, int64_t ray_begin, const float* ts, uint64_t seed,
               uint64_t offset, int64_t B, int N, float tn, float tf, const void* packed, float* rgb, float* disp, float* acc,
-              cudaStream_t s) {
+              int fold, cudaStream_t s) {
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
   NB_TRY_RC(ensure_attr(&DeviceState::attr_render, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<FwdEpi<false, true, true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kCSmemLaunch));
     return NB200_OK;
   }));
@@ -554,19 +681,21 @@ int tc_render(const float* rays, const float* poses, int H, int W, float f, int6
   p.rgb = rgb; p.disp = disp; p.acc = acc; p.B = B;
   p.sampler = ts ? 0 : 1; p.seed = seed; p.offset = offset; p.tn = tn; p.tf = tf;
   p.poses = poses; p.H = H; p.W = W; p.f = f; p.ray_begin = ray_begin;
-  chain_kernel<FwdEpi<false, true>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(p);
+  if (fold) chain_kernel<FwdEpi<false, true, true>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(p);
+  else chain_kernel<FwdEpi<false, true>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(p);
   NB_LAUNCH_CHECK("chain_kernel<FwdEpi<render>>");
   return NB200_OK;
 }
 
 int tc_backward(int, const float*, const float*, int64_t M, int, const void* packed, const float* d_out,
-                const void* saved, float* const* G, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+                const void* saved, float* const* G, void* scratch, size_t scratch_bytes, int fold, cudaStream_t s) {
   NB_TRY_RC(check_arch());
   NB_TRY_RC(ensure_layout());
   if (!scratch || scratch_bytes < tc_scratch_bytes(M, 1)) return NB200_ERR_WORKSPACE;
   NB_TRY_RC(ensure_attr(&DeviceState::attr_bwd, []() -> int {
     NB_CUDA_CHECK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemLaunch));
-    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
+    NB_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<DgradEpi<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemLaunch));
     return NB200_OK;
   }));
   const int64_t T = train_tiles(M);
@@ -583,7 +712,8 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     TmapPair tm;
     NB_TRY_RC(get_tmaps(packed, &tm));
     bp.tmap128 = tm.m128; bp.tmap64 = tm.m64;
-    chain_kernel<DgradEpi><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
+    if (fold) chain_kernel<DgradEpi<true>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
+    else chain_kernel<DgradEpi<false>><<<chain_grid(T), kCThreads, kCSmemLaunch, s>>>(bp);
     NB_LAUNCH_CHECK("chain_kernel<DgradEpi>");
   }
   // 2. weight gradients: (delta tensor, input tensor) pairs
@@ -619,11 +749,19 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
       w.cost += w.x_chunks * 16;
     }
   };
-  item(0, 8, L_C0, kHidden + kPosD, 0, kHidden, kHidden / 2, true);        // color_fc.0 <- g
-  item(0, 11, L_C0, kHidden + kPosD, kHidden, kPosD, kHidden / 2, false);  // color_fc.0 <- posd
-  head(2, 9, L_C1);                                                         // color_fc.2 <- c1 (CUDA cores)
-  item(1, 7, L_2, kHidden, 0, kHidden, kHidden, true);                      // layers_2   <- h7
-  head(1, 7, L_SIGMA);                                                      // sigma_fc   <- h7 (CUDA cores)
+  if (fold) {
+    item(0, 7, L_C0, kHidden + kPosD, 0, kHidden, kHidden / 2, true);      // Gm = delta_c1^T h7 -> pad image of color_fc.0
+    wp.items[n - 1].db = pad + kPadFoldS;                                   //   column sums of delta_c1 (un-folded below)
+    head(1, 7, L_SIGMA);                                                    // sigma_fc   <- h7 (CUDA cores)
+    item(0, 11, L_C0, kHidden + kPosD, kHidden, kPosD, kHidden / 2, false);  // color_fc.0 <- posd
+    head(2, 9, L_C1);                                                       // color_fc.2 <- c1 (CUDA cores)
+  } else {
+    item(0, 8, L_C0, kHidden + kPosD, 0, kHidden, kHidden / 2, true);        // color_fc.0 <- g
+    item(0, 11, L_C0, kHidden + kPosD, kHidden, kPosD, kHidden / 2, false);  // color_fc.0 <- posd
+    head(2, 9, L_C1);                                                         // color_fc.2 <- c1 (CUDA cores)
+    item(1, 7, L_2, kHidden, 0, kHidden, kHidden, true);                      // layers_2   <- h7
+    head(1, 7, L_SIGMA);                                                      // sigma_fc   <- h7 (CUDA cores)
+  }
   item(2, 6, L1_1, kHidden, 0, kHidden, kHidden, true);                     // layers_1.2 <- h6
   item(3, 5, L1_0, kHidden, 0, kHidden, kHidden, true);                     // layers_1.0 <- h5
   item(4, 4, L_SKIP, kHidden + kPosX, 0, kHidden, kHidden, true);           // skip       <- h4
@@ -640,7 +778,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     WItem& w = wp.items[i];
     const int chunks = w.a_chunks + w.b_chunks + w.x_chunks;
     int c = chunks == 8 ? 100 : (chunks == 6 ? 85 : (w.db ? 85 : 77));
-    if (w.head == 1) c = 124;
+    if (w.head == 1) c = chunks == 8 ? 124 : 106;   // (the 6-chunk carrier of the folded chain: scaled, not measured)
     if (w.head == 2) c = 83;
     w.cost = c;
   }
@@ -650,8 +788,14 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   wp.num_items = n;
   mlp_wgrad_tc_kernel<<<sm_count(), kWgThreads, kWgSmemLaunch, s>>>(wp);
   NB_LAUNCH_CHECK("mlp_wgrad_tc_kernel");
-  unpad_add_kernel<<<((int)kPadFloats + 255) / 256, 256, 0, s>>>(pad, G[2 * L_C0], G[2 * L_SKIP], G[2 * L0_0]);
+  unpad_add_kernel<<<((int)kPadFoldS + 255) / 256, 256, 0, s>>>(pad, G[2 * L_C0], G[2 * L_SKIP], G[2 * L0_0], fold);
   NB_LAUNCH_CHECK("unpad_add_kernel");
+  if (fold) {
+    fold_grads_kernel<<<(128 * 256 + 256 * 256 + 256 + 128 + 255) / 256, 256, 0, s>>>(
+        pad, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + h_layout.f32_off), G[2 * L_C0], G[2 * L_C0 + 1],
+        G[2 * L_2], G[2 * L_2 + 1]);
+    NB_LAUNCH_CHECK("fold_grads_kernel");
+  }
   return NB200_OK;
 }
 

@@ -50,7 +50,7 @@ class FrameRenderer:
                     e0.record()
                 rgb, disp, _ = ops.render_fused(self.net, self.N, poses=poses_dev, H=self.H, W=self.W, f=self.f,
                                                 ray_begin=ray_begin, n_rays=n_rays, tn=self.tn, tf=self.tf,
-                                                seed=self.seed, offset=self._offset)
+                                                seed=self.seed, offset=self._offset, precision=self.precision)
                 if time_mlp:
                     e1.record()
                     self.mlp_events.append((e0, e1))

@@ -14,7 +14,7 @@ import torch
 from . import _lib, config
 
 NUM_PARAMS = 595844
-_PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16, "bf16x3": _lib.BF16X3}
+_PREC = {"fp32": _lib.FP32, "bf16": _lib.BF16, "bf16x3": _lib.BF16X3, "bf16_layerwise": _lib.BF16_LAYERWISE}
 
 
 def flat_views(flat, shapes):
@@ -249,11 +249,11 @@ FUSED_RENDER_N = (32, 64, 128)     # whole rays per 128-sample tile
 
 def fused_render_supported(net, N, precision=None) -> bool:
     precision = precision or getattr(net, "precision", None) or config.get_precision()
-    return precision == "bf16" and int(N) in FUSED_RENDER_N
+    return precision in ("bf16", "bf16_layerwise") and int(N) in FUSED_RENDER_N
 
 
 def render_fused(net, N, rays=None, ts=None, poses=None, H=0, W=0, f=0.0, ray_begin=0, n_rays=None,
-                 tn=2.0, tf=6.0, seed=None, offset=None):
+                 tn=2.0, tf=6.0, seed=None, offset=None, precision=None):
     """No-grad render_nerf (utils/rendering.py:13-45) as ONE kernel: sampler -> posenc + MLP -> compositing.
     Either `rays` [B,6] (optionally with `ts` [B,N]; else Philox depths keyed by (seed, offset)), or a
     camera (`poses` [P,4,4], H, W, f, ray_begin, n_rays) whose rays are generated in the kernel.
@@ -262,7 +262,10 @@ def render_fused(net, N, rays=None, ts=None, poses=None, H=0, W=0, f=0.0, ray_be
     params = net.kernel_params()
     _lib.require_cuda(params[0], "Nerf parameters (call net.cuda())")
     dev = params[0].device
-    packed = net._packed.get(params, _lib.BF16)
+    prec = _PREC[precision or getattr(net, "precision", None) or config.get_precision()]
+    if prec not in _lib.BF16_MODES:
+        raise ValueError("render_fused needs a bf16 precision mode")
+    packed = net._packed.get(params, prec)
     if rays is not None:
         rays = _f32c(rays, "rays")
         B = rays.shape[0]
@@ -282,11 +285,11 @@ def render_fused(net, N, rays=None, ts=None, poses=None, H=0, W=0, f=0.0, ray_be
     acc = torch.empty((B,), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr(dev)
     if rays is not None:
-        rc = lib.nb200_render_rays(_lib.BF16, _lib.ptr(rays), _lib.ptr(ts), int(seed or 0), int(offset or 0), B, int(N),
+        rc = lib.nb200_render_rays(prec, _lib.ptr(rays), _lib.ptr(ts), int(seed or 0), int(offset or 0), B, int(N),
                                    float(tn), float(tf), _lib.ptr(packed), _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), st)
         _lib.check(rc, "nb200_render_rays")
     else:
-        rc = lib.nb200_render_camera(_lib.BF16, _lib.ptr(poses), poses.shape[0], int(H), int(W), float(f), int(ray_begin), B,
+        rc = lib.nb200_render_camera(prec, _lib.ptr(poses), poses.shape[0], int(H), int(W), float(f), int(ray_begin), B,
                                      int(seed or 0), int(offset or 0), int(N), float(tn), float(tf), _lib.ptr(packed),
                                      _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), st)
         _lib.check(rc, "nb200_render_camera")

@@ -18,7 +18,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     net = Nerf().cuda()
     poses = torch.stack(poses_to_render(4, -30, 25)).cuda()
     rays = ops.generate_rays(poses, 400, 400, 555.5); gt = torch.rand(rays.shape[0], 3, device="cuda")
-    tr = Trainer(net, rays, gt, N=64, batch_size=4096)
+    tr = Trainer(net, rays, gt, N=64, batch_size=4096, precision=os.environ.get("AB_PRECISION", "bf16"))
     for _ in range(30): tr.step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,7 +30,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     for _ in range(20): tr.step(time_parts=True)
     torch.cuda.synchronize()
     f = np.mean([e[0].elapsed_time(e[1]) for e in tr.part_events]); b = np.mean([e[2].elapsed_time(e[3]) for e in tr.part_events])
-    print(f"{os.path.basename(_lib.LIB_PATH):28s} step {step:7.4f} ms   fwd+save {f:7.4f}   bwd {b:7.4f}", flush=True)
+    print(f"{os.path.basename(_lib.LIB_PATH):20s} {os.environ.get('AB_PRECISION', 'bf16'):15s} step {step:7.4f} ms   fwd+save {f:7.4f}   bwd {b:7.4f}", flush=True)
 else:
     for lib in sys.argv[1:]:
         subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=dict(os.environ, NERF_B200_LIB=os.path.abspath(lib)))
