@@ -282,31 +282,98 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(ParamPtrs P, float* __res
   f[i] = v;
 }
 
+// One 32 x 64 tile of C (+)= A B in fp32 on CUDA cores, 256 threads (thread = 2 rows x 4 columns), K in chunks of 32
+// through shared memory with the next chunk's global loads in flight during the FMAs.  A(m, k) = a[m lda + k], or
+// a[k lda + m] when kTransA.  The fold / un-fold GEMMs are 8-17 MFLOP: what matters is their latency inside the step
+// (one thread per output with a 256-long dependent FMA chain took 35 us and 20 us; these take a few us).
+template <bool kTransA, bool kAccum>
+__device__ __forceinline__ void sgemm_tile_32x64(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                 float* __restrict__ c, int ldc, int K, int m0, int n0, const float* __restrict__ r1a,
+                                                 const float* __restrict__ r1b, float (*sA)[33], float (*sB)[64]) {
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float ra[4], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = t + 256 * r;
+      const int m = kTransA ? (idx & 31) : (idx >> 5), k = kTransA ? (idx >> 5) : (idx & 31);
+      ra[r] = kTransA ? __ldg(a + (size_t)(k0 + k) * lda + m0 + m) : __ldg(a + (size_t)(m0 + m) * lda + k0 + k);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = t + 256 * r;
+      rb[r] = __ldg(b + (size_t)(k0 + (idx >> 6)) * ldb + n0 + (idx & 63));
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    __syncthreads();   // the previous chunk has been consumed
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = t + 256 * r;
+      sA[kTransA ? (idx & 31) : (idx >> 5)][kTransA ? (idx >> 5) : (idx & 31)] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = t + 256 * r;
+      sB[idx >> 6][idx & 63] = rb[r];
+    }
+    __syncthreads();
+    if (k0 + 32 < K) fetch(k0 + 32);
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = sA[2 * ty][kk], a1 = sA[2 * ty + 1][kk];
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][4 * tx]);
+      acc[0][0] = fmaf(a0, bv.x, acc[0][0]); acc[0][1] = fmaf(a0, bv.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, bv.z, acc[0][2]); acc[0][3] = fmaf(a0, bv.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, bv.x, acc[1][0]); acc[1][1] = fmaf(a1, bv.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, bv.z, acc[1][2]); acc[1][3] = fmaf(a1, bv.w, acc[1][3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int m = m0 + 2 * ty + r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = n0 + 4 * tx + q;
+      float v = acc[r][q];
+      if (r1a) v = fmaf(__ldg(r1a + m), __ldg(r1b + n), v);   // + rank-1 term
+      float* dst = c + (size_t)m * ldc + n;
+      *dst = kAccum ? *dst + v : v;
+    }
+  }
+}
+
 // Folded weight and bias in fp32 (see the top of the file), plus the fp32 copies the gradient un-folding reads.
-// 65,536 threads; a 128 x 256 x 256 GEMM on CUDA cores is ~2 us of an optimizer step.
+// blocks 0..15: Wf = Wc0[:, :256] Wg in 32 x 64 tiles; blocks 16..31: bf (one warp per row); the rest: copies.
+constexpr int kFoldWBlocks = 16 + 16 + 96;
 __global__ void __launch_bounds__(256) fold_weights_kernel(ParamPtrs P, float* __restrict__ f) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sA[32][33];
+  __shared__ __align__(16) float sB[32][64];
   const float* Wc0 = P.p[2 * L_C0];
   const float* Wg = P.p[2 * L_2];
   const float* bg = P.p[2 * L_2 + 1];
   constexpr int ldc = kHidden + kPosD;
-  if (t < 128 * 256) {
-    const int i = t >> 8, j = t & 255;
+  const int b = (int)blockIdx.x;
+  if (b < 16) {
+    sgemm_tile_32x64<false, false>(Wc0, ldc, Wg, kHidden, f + kF32Wf, kHidden, kHidden, (b >> 2) * 32, (b & 3) * 64, nullptr, nullptr, sA, sB);
+  } else if (b < 32) {
+    const int i = (b - 16) * 8 + ((int)threadIdx.x >> 5), lane = (int)threadIdx.x & 31;
     float acc = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Wc0 + i * ldc + k), __ldg(Wg + k * kHidden + j), acc);
-    f[kF32Wf + t] = acc;
-    f[kF32Wc0g + t] = __ldg(Wc0 + i * ldc + j);
-  }
-  if (t < 256 * 256) f[kF32WgT + t] = __ldg(Wg + (t & 255) * kHidden + (t >> 8));   // [k][j] = Wg[j][k]
-  if (t < 256) {
-    f[kF32Bg + t] = __ldg(bg + t);
-    float acc = 0.f;
-    if (t < 128) {
-      acc = __ldg(P.p[2 * L_C0 + 1] + t);
-      for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Wc0 + t * ldc + k), __ldg(bg + k), acc);
+    for (int k = lane; k < kHidden; k += 32) acc = fmaf(__ldg(Wc0 + i * ldc + k), __ldg(bg + k), acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+      f[kF32Bias + kFoldBiasRow * 256 + i] = acc + __ldg(P.p[2 * L_C0 + 1] + i);
+      f[kF32Bias + kFoldBiasRow * 256 + 128 + i] = 0.f;
     }
-    f[kF32Bias + kFoldBiasRow * 256 + t] = acc;
+  } else {
+    for (int t = (b - 32) * 256 + (int)threadIdx.x; t < 256 * 256; t += 96 * 256) {
+      f[kF32WgT + t] = __ldg(Wg + (t & 255) * kHidden + (t >> 8));   // [k][j] = Wg[j][k]
+      if (t < 128 * 256) f[kF32Wc0g + t] = __ldg(Wc0 + (t >> 8) * ldc + (t & 255));
+      if (t < 256) f[kF32Bg + t] = __ldg(bg + t);
+    }
   }
 }
 
@@ -435,33 +502,31 @@ __global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict_
 
 // Folded chain: gradients of color_fc.0[:, :256], layers_2 and their biases from Gm = delta_c1^T h7 (pad image of
 // color_fc.0, columns 0..255) and s = column sums of delta_c1 (see the top of the file).  `f` = the packed buffer's
-// fp32 tail (Wg^T, Wc0[:, :256], bg as they were at pack time).  98,688 threads, ~17 MFLOP.
+// fp32 tail (Wg^T, Wc0[:, :256], bg as they were at pack time).  blocks 0..15: dWc0[:, :256] += Gm Wg^T + s bg^T;
+// blocks 16..47: dWg += Wc0[:, :256]^T Gm; block 48: dbg += Wc0[:, :256]^T s and dbc0 += s.
+constexpr int kFoldGBlocks = 16 + 32 + 1;
 __global__ void __launch_bounds__(256) fold_grads_kernel(const float* __restrict__ pad, const float* __restrict__ f,
                                                          float* __restrict__ gC0, float* __restrict__ gbC0,
                                                          float* __restrict__ gL2, float* __restrict__ gbL2) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sA[32][33];
+  __shared__ __align__(16) float sB[32][64];
   const float* Gm = pad + kPadC0;
   const float* sv = pad + kPadFoldS;
-  if (t < 128 * 256) {                       // dWc0[i, j] += sum_k Gm[i, k] Wg[j, k] + s[i] bg[j]
-    const int i = t >> 8, j = t & 255;
-    float acc = __ldg(sv + i) * __ldg(f + kF32Bg + j);
-#pragma unroll 8
-    for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(Gm + i * kPadPitchWide + k), __ldg(f + kF32WgT + k * kHidden + j), acc);
-    gC0[i * (kHidden + kPosD) + j] += acc;
-  } else if (t < 128 * 256 + 256 * 256) {    // dWg[j, k] += sum_i Wc0[i, j] Gm[i, k]
-    const int u = t - 128 * 256, j = u >> 8, k = u & 255;
+  const int b = (int)blockIdx.x;
+  if (b < 16) {
+    sgemm_tile_32x64<false, true>(Gm, kPadPitchWide, f + kF32WgT, kHidden, gC0, kHidden + kPosD, kHidden, (b >> 2) * 32, (b & 3) * 64,
+                                  sv, f + kF32Bg, sA, sB);
+  } else if (b < 48) {
+    const int u = b - 16;
+    sgemm_tile_32x64<true, true>(f + kF32Wc0g, kHidden, Gm, kPadPitchWide, gL2, kHidden, 128, (u >> 2) * 32, (u & 3) * 64, nullptr, nullptr,
+                                 sA, sB);
+  } else {
+    const int j = (int)threadIdx.x;
     float acc = 0.f;
 #pragma unroll 8
-    for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(f + kF32Wc0g + i * kHidden + j), __ldg(Gm + i * kPadPitchWide + k), acc);
-    gL2[j * kHidden + k] += acc;
-  } else if (t < 128 * 256 + 256 * 256 + 256) {   // dbg[j] += sum_i Wc0[i, j] s[i]
-    const int j = t - (128 * 256 + 256 * 256);
-    float acc = 0.f;
     for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(f + kF32Wc0g + i * kHidden + j), __ldg(sv + i), acc);
     gbL2[j] += acc;
-  } else if (t < 128 * 256 + 256 * 256 + 256 + 128) {
-    const int i = t - (128 * 256 + 256 * 256 + 256);
-    gbC0[i] += __ldg(sv + i);
+    if (j < 128) gbC0[j] += __ldg(sv + j);
   }
 }
 
@@ -471,7 +536,7 @@ int tc_pack_weights(const float* const* P, void* packed, int x3, cudaStream_t s)
   for (int i = 0; i < 24; ++i) pp.p[i] = P[i];
   const int nslabs = x3 ? h_layout.num_fwd3 : h_layout.num_fwd + h_layout.num_bwd + h_layout.num_fold;
   if (!x3) {
-    fold_weights_kernel<<<256, 256, 0, s>>>(pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + h_layout.f32_off));
+    fold_weights_kernel<<<kFoldWBlocks, 256, 0, s>>>(pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + h_layout.f32_off));
     NB_LAUNCH_CHECK("fold_weights_kernel");
   }
   if (x3) pack_slabs_kernel<true><<<nslabs * kPackSplit, 256, 0, s>>>(pp, reinterpret_cast<uint8_t*>(packed));
@@ -791,7 +856,7 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
   unpad_add_kernel<<<((int)kPadFoldS + 255) / 256, 256, 0, s>>>(pad, G[2 * L_C0], G[2 * L_SKIP], G[2 * L0_0], fold);
   NB_LAUNCH_CHECK("unpad_add_kernel");
   if (fold) {
-    fold_grads_kernel<<<(128 * 256 + 256 * 256 + 256 + 128 + 255) / 256, 256, 0, s>>>(
+    fold_grads_kernel<<<kFoldGBlocks, 256, 0, s>>>(
         pad, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + h_layout.f32_off), G[2 * L_C0], G[2 * L_C0 + 1],
         G[2 * L_2], G[2 * L_2 + 1]);
     NB_LAUNCH_CHECK("fold_grads_kernel");
