@@ -843,7 +843,10 @@ int tc_backward(int, const float*, const float*, int64_t M, int, const void* pac
     WItem& w = wp.items[i];
     const int chunks = w.a_chunks + w.b_chunks + w.x_chunks;
     int c = chunks == 8 ? 100 : (chunks == 6 ? 85 : (w.db ? 85 : 77));
-    if (w.head == 1) c = chunks == 8 ? 124 : 106;   // (the 6-chunk carrier of the folded chain: scaled, not measured)
+#ifndef NB_WG_HEAD6_COST
+#define NB_WG_HEAD6_COST 130   // same-box A/B of the train step: 90 -> 1.085 ms, 106 -> 1.041, 124 -> 1.020, 140 -> 1.021
+#endif
+    if (w.head == 1) c = chunks == 8 ? 124 : NB_WG_HEAD6_COST;   // (the 6-chunk carrier of the folded chain)
     if (w.head == 2) c = 83;
     w.cost = c;
   }
