@@ -113,8 +113,10 @@ int nb200_positional_encoding(const float* v, int64_t M, int Lp, int Ld, float* 
 /* (i) weight packing.  params: HOST array of 24 DEVICE pointers in state_dict order
  * (utils/nets.py:16-32; layers_0.0.weight, layers_0.0.bias, ..., color_fc.2.bias).
  * NB200_FP32 uses the parameters in place (packed may be NULL, bytes == 0).
- * NB200_BF16 writes the tcgen05 operand images (bf16, K-major, 128B-swizzled, padded/split
- * K: 63->64, 319->256+64, 283->256+32, plus the transposed images for dgrad) and fp32 biases. */
+ * NB200_BF16 / NB200_BF16_LAYERWISE write the tcgen05 operand images (bf16, K-major, 128B-swizzled,
+ * padded/split K: 63->64, 319->256+64, 283->256+32, plus the transposed images for dgrad), the slabs
+ * of the folded weight color_fc.0[:, :256] x layers_2 and an fp32 tail (biases, heads, and the fp32
+ * copies the backward un-folds gradients with): one image serves both modes. */
 size_t nb200_packed_weights_bytes(int precision);
 int nb200_pack_weights(int precision, const float* const* params, void* packed,
                        nb200_stream_t stream);
@@ -133,7 +135,9 @@ int nb200_mlp_forward(int precision, int in_mode, const float* in0, const float*
 /* (iii) MLP backward.  d_out dev [M,4] -> grads: HOST array of 24 DEVICE pointers (same order
  * and shapes as params; typically views into one flat 595,844-float buffer).  Gradients are
  * ACCUMULATED (+=) like autograd; zero them first for a fresh gradient.  No input gradient:
- * query points never require grad in the reference (rendering.py:39-41). */
+ * query points never require grad in the reference (rendering.py:39-41).
+ * `precision`, `packed` and `saved` must be the ones of the forward call this is the backward of
+ * (NB200_BF16 does not save layers_2's output; its backward reads the fp32 tail of `packed`). */
 int nb200_mlp_backward(int precision, int in_mode, const float* in0, const float* in1, int64_t M,
                        int N, const float* const* params, const void* packed, const float* d_out,
                        const void* saved, float* const* grads, void* scratch,
