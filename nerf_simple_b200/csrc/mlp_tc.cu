@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) fold_weights_kernel(ParamPtrs P, float* _
 constexpr int kTileM = 128;                               // samples per tile (= TMEM lanes)
 constexpr uint32_t kABytes = 65536, kEBytes = 16384;      // activation tile 128x256 bf16, encoding tile 128x64 bf16
 
-// saved activations (training): tensors 0..7 = h0..h7, 8 = g (256 cols, 64 KB per tile), 9 = c1
+// saved activations (training): tensors 0..7 = h0..h7, 8 = g (256 cols, 64 KB per tile; unwritten in the folded chain), 9 = c1
 // (128 cols, 32 KB per tile), 10 = posx (64 cols, 16 KB), 11 = posd (32 of 64 cols, 16 KB).  Every
 // tile is stored as [K-block][128 rows x 128 B SWIZZLE_128B], i.e. exactly the UMMA operand image
 // the backward kernels bulk-copy back into shared memory (K-major for dgrad, MN-major for wgrad).

@@ -4,7 +4,10 @@
 //       per 128-sample tile it walks color_fc.0 -> layers_2 -> layers_1 -> skip -> layers_0 backwards,
 //       delta_in = (delta_out @ W) * relu'(saved activation), each delta kept in shared memory as
 //       the A operand of the next MMA and written once to HBM (bf16 tile image) for wgrad.
-//   mlp_wgrad_tc_kernel : dW = delta^T @ activation for the 12 (delta, input) pairs.  Both operands
+//       (DgradEpi<true>, the default: layers_2 is folded into color_fc.0, so delta_h7 comes from delta_c1 in ONE layer
+//       and delta_g does not exist -- mlp_tc.cu, top.)
+//   mlp_wgrad_tc_kernel : dW = delta^T @ activation for the 12 (delta, input) pairs (11 in the folded chain, where
+//       Gm = delta_c1^T h7 replaces the pairs of color_fc.0 <- g and layers_2 <- h7).  Both operands
 //       are the saved tile images read as MN-major UMMA operands (K = samples); accumulators live in
 //       TMEM across the CTA's whole tile range, bias gradients are column sums taken from the staged
 //       delta tiles by otherwise idle warps, one atomic flush per (CTA, layer) segment.
@@ -12,7 +15,8 @@
 //       cores) while h7 / c1 are staged, so the heads need no pass of their own.
 
 // ------------------------------------------------------------------ delta scratch layout
-// tensor 0 = delta_c1 (128 cols, 32 KB/tile); tensors 1..9 = delta_g, delta_h7, ..., delta_h0 (64 KB/tile)
+// tensor 0 = delta_c1 (128 cols, 32 KB/tile); tensors 1..9 = delta_g, delta_h7, ..., delta_h0 (64 KB/tile).
+// The folded chain keeps this layout and leaves tensor 1 unwritten.
 constexpr size_t kDeltaTileBytes = 32768 + 9 * 65536;
 __host__ __device__ __forceinline__ size_t delta_tensor_off(int t, int64_t num_tiles) {
   return (t == 0 ? (size_t)0 : (size_t)32768 + (size_t)(t - 1) * 65536) * (size_t)num_tiles;
